@@ -1,0 +1,117 @@
+/*
+ * sinc_b200.h -- C ABI of the B200-native SincConv hot path (libsinc_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of MarvelMathesh/sincformer-metacog-speech-enhancement:
+ * the Perception Agent's SincNet front-end, agents/perception.py::SincConv1d, forward and backward.
+ * The reference has no FFI of its own (it is pure PyTorch); each entry point below cites the
+ * reference code it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all launches are
+ *     asynchronous on it, the library never synchronises the device;
+ *   - the library allocates nothing and frees nothing: the caller owns x, y, grads and the
+ *     workspace (size from sinc_workspace_bytes), and may reuse the workspace across calls that
+ *     are ordered on one stream;
+ *   - return value: 0 = success, < 0 = argument error (SINC_E_*), > 0 = a cudaError_t;
+ *     sinc_strerror() turns either into text.  Nothing throws or exits across this boundary;
+ *   - C = out_channels, K = kernel_size (odd; the reference bumps even K to K+1 in __init__,
+ *     agents/perception.py:44-45 -- the host mirror does the same before calling in),
+ *     H = (K-1)/2, x is (B,1,T) with unit time stride and x_stride_b elements between rows,
+ *     y / grad_y are (B,C,T) contiguous, filter-major per utterance (strides C*T, T, 1).
+ *   - element types: SINC_DTYPE_F32 (0) or SINC_DTYPE_BF16 (1) for y and grad_y; everything else fp32.
+ */
+#ifndef SINC_B200_H_
+#define SINC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SINC_ABI_VERSION 1
+
+#define SINC_DTYPE_F32 0
+#define SINC_DTYPE_BF16 1
+
+/* kernel-family selector for sinc_set_engine(): 0 = pick the fastest supported for the shape
+ * (default), 1 = FP32 FMA kernels only, 2 = tcgen05 tensor-core kernels only (error if the shape is
+ * not supported).  Every engine is hand-written sm_100a CUDA; there is no CPU path. */
+#define SINC_ENGINE_AUTO 0
+#define SINC_ENGINE_FMA 1
+#define SINC_ENGINE_TC 2
+
+#define SINC_OK 0
+#define SINC_E_NULL (-1)        /* a required pointer is NULL                               */
+#define SINC_E_SHAPE (-2)       /* B, T, C or K out of range (K must be odd, all >= 1)      */
+#define SINC_E_DTYPE (-3)       /* unknown element type code                                */
+#define SINC_E_WORKSPACE (-4)   /* workspace NULL or smaller than sinc_workspace_bytes()    */
+#define SINC_E_UNSUPPORTED (-5) /* shape too large for on-chip filter storage (see DESIGN)  */
+#define SINC_E_ALIGN (-6)       /* a pointer is not aligned to its element type             */
+#define SINC_E_DEVICE (-7)      /* current device is not compute capability 10.x            */
+#define SINC_E_ENGINE (-8)      /* requested engine cannot run this shape                   */
+
+/* The four small state tensors of the module plus its scalar attributes.
+ * Replaces: the attributes/parameters/buffers set up in SincConv1d.__init__
+ * (agents/perception.py:35-77): low_hz_ (C,1), band_hz_ (C,1), window (K,), n_ (1,H). */
+typedef struct sinc_filterbank {
+  const float* low_hz;   /* (C)   parameter low_hz_                                   */
+  const float* band_hz;  /* (C)   parameter band_hz_                                  */
+  const float* window;   /* (K)   buffer window                                       */
+  const float* n;        /* (H)   buffer n_  (may be NULL when K == 1)                */
+  int32_t C;
+  int32_t K;
+  double sample_rate;    /* module attribute sample_rate                              */
+  double min_low_hz;     /* module attribute min_low_hz                               */
+  double min_band_hz;    /* module attribute min_band_hz                              */
+} sinc_filterbank;
+
+int sinc_abi_version(void);
+const char* sinc_strerror(int code);
+
+/* Number of kernels this library has launched in this process (monotonic; for bench accounting). */
+uint64_t sinc_kernel_launch_count(void);
+
+/* Select the kernel family for subsequent calls from this process (SINC_ENGINE_*). */
+int sinc_set_engine(int engine);
+int sinc_get_engine(void);
+/* Which engine the last successful sinc_forward / sinc_backward call on this thread actually used:
+ * bit 0 forward, bit 1 grad-input, bit 2 grad-filter; a set bit means tcgen05, clear means FMA. */
+int sinc_last_engine_mask(void);
+
+/* Bytes of device scratch sinc_forward / sinc_backward need for this shape (never 0). */
+size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K);
+
+/* Filter synthesis alone: parameters -> (C,K) fp32 filter bank, row-major.
+ * Replaces agents/perception.py:89-115 (the part of SincConv1d.forward before F.conv1d).
+ * Debug / test entry point: the convolution kernels synthesise in their own prologue and never
+ * read this output. */
+int sinc_synthesize(const sinc_filterbank* fb, float* filters_out, void* stream);
+
+/* Forward: y[b,c,t] = sum_k w[c,k] * x[b,t+k-H], zero padded, stride 1.
+ * Replaces SincConv1d.forward (agents/perception.py:79-118) = synthesis + F.conv1d(stride=1,
+ * padding=K//2).  y_dtype selects fp32 or bf16 storage of y (math is fp32 either way). */
+int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, void* y,
+                 int32_t y_dtype, int64_t B, int64_t T, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Backward of sinc_forward.
+ * Replaces autograd's ConvolutionBackward0 of agents/perception.py:117-118 (grad-input, grad-filter)
+ * followed by the backward of the synthesis graph agents/perception.py:89-115 (grad low_hz_/band_hz_).
+ *   grad_y      (B,C,T) in gy_dtype
+ *   grad_x      (B,T) fp32, row stride T, or NULL to skip grad-input (waveform.requires_grad False)
+ *   grad_low, grad_band  (C) fp32, or both NULL to skip the parameter gradients
+ *   grad_filters (C,K) fp32 or NULL: the intermediate dL/dw, exposed for parity tests.
+ * The (C,K) reduction order is fixed by the shape (bitwise reproducible run to run); the synthesis
+ * chain rule is evaluated in fp64 ("why fp64"). */
+int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, const void* grad_y,
+                  int32_t gy_dtype, float* grad_x, float* grad_low, float* grad_band,
+                  float* grad_filters, int64_t B, int64_t T, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SINC_B200_H_ */

@@ -1,0 +1,175 @@
+// C ABI of libsinc_b200.so: argument validation, engine selection, launch accounting.
+// Declarations and the reference code each entry point replaces: include/sinc_b200.h.
+#include <atomic>
+#include <mutex>
+
+#include "sinc_internal.h"
+
+namespace sinc {
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
+static thread_local int t_last_mask = 0;
+
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int get_device_info(DeviceInfo* out) {
+  static std::mutex mu;
+  static DeviceInfo cache[64];
+  static bool have[64] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return (int)e;
+  if (dev < 0 || dev >= 64) return SINC_E_DEVICE;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!have[dev]) {
+    DeviceInfo di;
+    if ((e = cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&di.cc_major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&di.cc_minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
+      return (int)e;
+    cache[dev] = di;
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  return 0;
+}
+
+WorkspaceLayout workspace_layout(int C, int K) {
+  WorkspaceLayout wl;
+  wl.Cpad = round_up(C, kChanBlock);
+  wl.Kpad = round_up(K, kTapBlock);
+  wl.partial_bytes = (size_t)kMaxPartialSlots * wl.Cpad * wl.Kpad * sizeof(float);
+  wl.total_bytes = (wl.partial_bytes + 255) / 256 * 256 + 256;
+  return wl;
+}
+
+static int check_bank(const sinc_filterbank* fb) {
+  if (!fb || !fb->low_hz || !fb->band_hz || !fb->window) return SINC_E_NULL;
+  if (fb->C < 1 || fb->K < 1 || (fb->K % 2) == 0) return SINC_E_SHAPE;
+  if (fb->K > 1 && !fb->n) return SINC_E_NULL;
+  return 0;
+}
+
+static int check_device(DeviceInfo* di) {
+  int r = get_device_info(di);
+  if (r != 0) return r;
+  if (di->cc_major != 10) return SINC_E_DEVICE;
+  return 0;
+}
+
+}  // namespace sinc
+
+using namespace sinc;
+
+extern "C" {
+
+int sinc_abi_version(void) { return SINC_ABI_VERSION; }
+
+const char* sinc_strerror(int code) {
+  switch (code) {
+    case SINC_OK: return "success";
+    case SINC_E_NULL: return "sinc: a required pointer is NULL";
+    case SINC_E_SHAPE: return "sinc: bad shape (need B,T,C >= 1 and odd K >= 1)";
+    case SINC_E_DTYPE: return "sinc: unknown element type code";
+    case SINC_E_WORKSPACE: return "sinc: workspace missing or smaller than sinc_workspace_bytes()";
+    case SINC_E_UNSUPPORTED: return "sinc: kernel_size too large for on-chip filter storage";
+    case SINC_E_ALIGN: return "sinc: pointer not aligned to its element type";
+    case SINC_E_DEVICE: return "sinc: current device is not an sm_100-class (compute capability 10.x) GPU";
+    case SINC_E_ENGINE: return "sinc: the requested engine cannot run this shape";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  return "sinc: unknown error";
+}
+
+uint64_t sinc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int sinc_set_engine(int engine) {
+  if (engine < SINC_ENGINE_AUTO || engine > SINC_ENGINE_TC) return SINC_E_ENGINE;
+  g_engine.store(engine);
+  return 0;
+}
+int sinc_get_engine(void) { return g_engine.load(); }
+int sinc_last_engine_mask(void) { return t_last_mask; }
+
+size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K) {
+  (void)B;
+  (void)T;
+  if (C < 1) C = 1;
+  if (K < 1) K = 1;
+  return workspace_layout(C, K).total_bytes;
+}
+
+int sinc_synthesize(const sinc_filterbank* fb, float* filters_out, void* stream) {
+  int r = check_bank(fb);
+  if (r) return r;
+  if (!filters_out) return SINC_E_NULL;
+  DeviceInfo di;
+  if ((r = check_device(&di))) return r;
+  return (int)launch_synthesize(to_bank(fb), filters_out, (cudaStream_t)stream);
+}
+
+int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, void* y, int32_t y_dtype,
+                 int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream) {
+  int r = check_bank(fb);
+  if (r) return r;
+  if (!x || !y) return SINC_E_NULL;
+  if (B < 1 || T < 1) return SINC_E_SHAPE;
+  if (y_dtype != SINC_DTYPE_F32 && y_dtype != SINC_DTYPE_BF16) return SINC_E_DTYPE;
+  if (reinterpret_cast<uintptr_t>(x) % 4 || reinterpret_cast<uintptr_t>(y) % (y_dtype == SINC_DTYPE_F32 ? 4 : 2))
+    return SINC_E_ALIGN;
+  (void)workspace;
+  (void)workspace_bytes;
+  DeviceInfo di;
+  if ((r = check_device(&di))) return r;
+  const Bank bank = to_bank(fb);
+  const int engine = g_engine.load();
+  if (engine == SINC_ENGINE_TC) return SINC_E_ENGINE;  // tcgen05 forward: see sinc_tc.cu (not built yet)
+  if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
+  cudaError_t e = launch_fwd_fma(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  t_last_mask = (t_last_mask & ~1);
+  return 0;
+}
+
+int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, const void* grad_y,
+                  int32_t gy_dtype, float* grad_x, float* grad_low, float* grad_band, float* grad_filters,
+                  int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream) {
+  int r = check_bank(fb);
+  if (r) return r;
+  if (!grad_y) return SINC_E_NULL;
+  if ((grad_low == nullptr) != (grad_band == nullptr)) return SINC_E_NULL;
+  const bool want_params = grad_low != nullptr || grad_filters != nullptr;
+  if (want_params && !x) return SINC_E_NULL;
+  if (B < 1 || T < 1) return SINC_E_SHAPE;
+  if (gy_dtype != SINC_DTYPE_F32 && gy_dtype != SINC_DTYPE_BF16) return SINC_E_DTYPE;
+  if (reinterpret_cast<uintptr_t>(grad_y) % (gy_dtype == SINC_DTYPE_F32 ? 4 : 2)) return SINC_E_ALIGN;
+  DeviceInfo di;
+  if ((r = check_device(&di))) return r;
+  const Bank bank = to_bank(fb);
+  const int engine = g_engine.load();
+  if (engine == SINC_ENGINE_TC) return SINC_E_ENGINE;
+  if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  if (grad_x) {
+    e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (want_params) {
+    const WorkspaceLayout wl = workspace_layout(bank.C, bank.K);
+    if (!workspace || workspace_bytes < wl.total_bytes) return SINC_E_WORKSPACE;
+    float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+    int slots = 0;
+    e = launch_bwd_filter_fma(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
+    if (e != cudaSuccess) return (int)e;
+    e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, grad_low, grad_band, grad_filters, st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  t_last_mask = (t_last_mask & 1);
+  return 0;
+}
+
+}  // extern "C"

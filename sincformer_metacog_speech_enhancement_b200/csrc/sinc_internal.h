@@ -1,0 +1,81 @@
+// Internal declarations shared by the translation units of libsinc_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sinc_b200.h"
+
+namespace sinc {
+
+// Device-side view of the module state (agents/perception.py:35-77) -- passed by value to kernels.
+struct Bank {
+  const float* low_hz;
+  const float* band_hz;
+  const float* window;
+  const float* n;
+  int C;
+  int K;
+  double sr;
+  double min_low;
+  double min_band;
+};
+
+inline Bank to_bank(const sinc_filterbank* fb) {
+  Bank b;
+  b.low_hz = fb->low_hz;
+  b.band_hz = fb->band_hz;
+  b.window = fb->window;
+  b.n = fb->n;
+  b.C = fb->C;
+  b.K = fb->K;
+  b.sr = fb->sample_rate;
+  b.min_low = fb->min_low_hz;
+  b.min_band = fb->min_band_hz;
+  return b;
+}
+
+struct DeviceInfo {
+  int sm_count;
+  int cc_major;
+  int cc_minor;
+  int max_smem_optin;
+};
+// Cached per device (immutable after first query).
+int get_device_info(DeviceInfo* out);
+
+void count_launch(int n = 1);
+
+// ---- tiling constants shared between workspace sizing and the kernels -------------------------
+constexpr int kChanBlock = 64;    // channels handled per CTA (filters kept in shared memory)
+constexpr int kTapBlock = 256;    // taps handled per grad-filter CTA
+constexpr int kMaxPartialSlots = 2 * 160;  // grad-filter partial tiles (2 CTAs/SM, <=160 SMs)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Workspace layout (all offsets 256-B aligned):
+//   [0, partial_bytes)  grad-filter partial tiles: slots x Cpad x Kpad fp32
+struct WorkspaceLayout {
+  int Cpad;         // C rounded up to kChanBlock
+  int Kpad;         // K rounded up to kTapBlock
+  size_t partial_bytes;
+  size_t total_bytes;
+};
+WorkspaceLayout workspace_layout(int C, int K);
+
+// ---- FP32-FMA engine (sinc_fma.cu) ---------------------------------------------------------------
+bool fma_supported(int C, int K, const DeviceInfo& di);
+cudaError_t launch_synthesize(const Bank& bank, float* filters_out, cudaStream_t st);
+cudaError_t launch_fwd_fma(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype,
+                           int64_t B, int64_t T, const DeviceInfo& di, cudaStream_t st);
+cudaError_t launch_bwd_input_fma(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B,
+                                 int64_t T, const DeviceInfo& di, cudaStream_t st);
+// writes `*slots_used` partial tiles into ws_partials
+cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy,
+                                  int gy_dtype, float* ws_partials, int* slots_used, int64_t B,
+                                  int64_t T, const DeviceInfo& di, cudaStream_t st);
+// reduces the partial tiles (fp64, fixed order) and applies the synthesis chain rule in fp64
+cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad,
+                            float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st);
+
+}  // namespace sinc

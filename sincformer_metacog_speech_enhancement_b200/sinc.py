@@ -1,0 +1,260 @@
+"""Drop-in replacement for the reference's ``agents.perception.SincConv1d`` on B200.
+
+Host-side mirror of the reference interface (same constructor arguments, attribute, parameter and
+buffer names, output layout); all arithmetic of forward and backward runs in libsinc_b200.so
+(hand-written sm_100a kernels behind the C ABI of include/sinc_b200.h).  There is no CPU path and no
+PyTorch-op fallback: a non-CUDA input raises.
+
+Reference (paths relative to the reference repository root):
+  * constructor / state ......... agents/perception.py:35-77
+  * forward ..................... agents/perception.py:79-118
+  * call site ................... agents/perception.py:152-156 (construction), :228-232 (call)
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_FALLBACK_SAMPLE_RATE = 8000  # reference config.py:17
+
+
+def _default_sample_rate():
+    """The reference falls back to ``config.SAMPLE_RATE`` when sample_rate is falsy
+    (agents/perception.py:41).  If the host application's ``config`` module is loaded, honour it."""
+    cfg = sys.modules.get("config")
+    rate = getattr(cfg, "SAMPLE_RATE", None) if cfg is not None else None
+    return rate or _FALLBACK_SAMPLE_RATE
+
+
+def _erb_rate(hz: float) -> float:
+    return 21.4 * math.log10(1 + hz / 228.7)
+
+
+def _erb_spaced_edges(n_filters: int, f_min: float, f_max: float) -> np.ndarray:
+    """n_filters+1 band edges, equally spaced on the ERB-rate scale (float64), in Hz
+    (agents/perception.py:52-59)."""
+    grid = np.linspace(_erb_rate(f_min), _erb_rate(f_max), n_filters + 1)
+    return 228.7 * (10 ** (grid / 21.4) - 1)
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return _lib.DTYPE_F32
+    if dt == torch.bfloat16:
+        return _lib.DTYPE_BF16
+    raise RuntimeError(f"SincConv1d: unsupported storage dtype {dt} (float32 or bfloat16)")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _bank(low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz):
+    fb = _lib.FilterBank()
+    fb.low_hz = low_hz_.data_ptr()
+    fb.band_hz = band_hz_.data_ptr()
+    fb.window = window.data_ptr()
+    fb.n = n_.data_ptr() if n_.numel() > 0 else 0
+    fb.C = low_hz_.numel()
+    fb.K = window.numel()
+    fb.sample_rate = float(sample_rate)
+    fb.min_low_hz = float(min_low_hz)
+    fb.min_band_hz = float(min_band_hz)
+    return fb
+
+
+def _small(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    if t.device != device:
+        raise RuntimeError(f"SincConv1d: {name} is on {t.device}, input is on {device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"SincConv1d: {name} must be float32 (got {t.dtype}); the B200 path computes "
+                           "in fp32 and does not follow .double()/.half() casts of the module")
+    return t.detach().contiguous()
+
+
+def _workspace(B, T, C, K, device):
+    nbytes = _lib.load().sinc_workspace_bytes(B, T, C, K)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device), nbytes
+
+
+class SincConvFunction(torch.autograd.Function):
+    """y = conv1d(x, synth(low_hz_, band_hz_; window, n_), stride=1, padding=K//2) with a hand-written
+    backward: grad-input plus the parameter gradients through the synthesis chain rule (fp64)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype):
+        lib = _lib.load()
+        if not x.is_cuda:
+            raise RuntimeError("SincConv1d (B200): input must be a CUDA tensor -- this implementation has no CPU path")
+        if x.dim() != 3 or x.shape[1] != 1:
+            raise RuntimeError(f"SincConv1d expects (batch, 1, samples); got {tuple(x.shape)}")
+        if x.dtype != torch.float32:
+            raise RuntimeError(f"SincConv1d: input must be float32 (got {x.dtype})")
+        dev = x.device
+        low = _small(low_hz_, "low_hz_", dev)
+        band = _small(band_hz_, "band_hz_", dev)
+        win = _small(window, "window", dev)
+        nn_ = _small(n_, "n_", dev)
+        C, K = low.numel(), win.numel()
+        if K % 2 == 0 or nn_.numel() != (K - 1) // 2 or band.numel() != C:
+            raise RuntimeError("SincConv1d: inconsistent low_hz_/band_hz_/window/n_ shapes")
+        xd = x.detach()
+        if xd.stride(2) != 1 and xd.shape[2] > 1:
+            xd = xd.contiguous()
+        B, _, T = xd.shape
+        if B == 0 or T == 0:
+            raise RuntimeError("SincConv1d: empty input")
+        y = torch.empty((B, C, T), dtype=out_dtype, device=dev)
+        fb = _bank(low, band, win, nn_, sample_rate, min_low_hz, min_band_hz)
+        ws, ws_bytes = _workspace(B, T, C, K, dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.sinc_forward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(y),
+                                  _dtype_code(out_dtype), B, T, _ptr(ws), ws_bytes, ctypes.c_void_p(stream))
+        _lib.check(rc, "sinc_forward")
+        ctx.save_for_backward(xd, low, band, win, nn_)
+        ctx.attrs = (float(sample_rate), float(min_low_hz), float(min_band_hz))
+        ctx.expose_grad_filters = getattr(SincConvFunction, "_expose_grad_filters", False)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, grad_y):
+        lib = _lib.load()
+        xd, low, band, win, nn_ = ctx.saved_tensors
+        sr, min_low, min_band = ctx.attrs
+        need_x = ctx.needs_input_grad[0]
+        need_p = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dev = xd.device
+        B, _, T = xd.shape
+        C, K = low.numel(), win.numel()
+        g = grad_y
+        if g.dtype not in (torch.float32, torch.bfloat16):
+            g = g.float()
+        g = g.contiguous()
+        gx = torch.empty((B, 1, T), dtype=torch.float32, device=dev) if need_x else None
+        gp = torch.empty((2, C, 1), dtype=torch.float32, device=dev) if need_p else None
+        gfilt = None
+        if need_p and ctx.expose_grad_filters:
+            gfilt = torch.empty((C, K), dtype=torch.float32, device=dev)
+        if need_x or need_p:
+            fb = _bank(low, band, win, nn_, sr, min_low, min_band)
+            ws, ws_bytes = _workspace(B, T, C, K, dev)
+            with torch.cuda.device(dev):
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                rc = lib.sinc_backward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(g),
+                                       _dtype_code(g.dtype), _ptr(gx), _ptr(gp[0] if need_p else None),
+                                       _ptr(gp[1] if need_p else None), _ptr(gfilt), B, T, _ptr(ws), ws_bytes,
+                                       ctypes.c_void_p(stream))
+            _lib.check(rc, "sinc_backward")
+        if gfilt is not None:
+            SincConvFunction._last_grad_filters = gfilt
+        g_low = gp[0] if need_p and ctx.needs_input_grad[1] else None
+        g_band = gp[1] if need_p and ctx.needs_input_grad[2] else None
+        return gx, g_low, g_band, None, None, None, None, None, None
+
+
+class SincConv1d(nn.Module):
+    """SincNet band-pass front-end, B200-native.  Same constructor, attributes, parameter names
+    (``low_hz_``, ``band_hz_``), buffer names (``window``, ``n_``), deterministic ERB-rate initialisation
+    and ``(batch, out_channels, samples)`` output as the reference ``agents.perception.SincConv1d``
+    (agents/perception.py:23-118), so state_dicts load in both directions.
+
+    Extra keyword-only argument ``out_dtype`` (float32 default, or bfloat16): storage type of the output
+    activation; the arithmetic is fp32 either way.
+    """
+
+    def __init__(self, out_channels, kernel_size, sample_rate=None, min_low_hz=50, min_band_hz=50,
+                 *, out_dtype=torch.float32):
+        super().__init__()
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size + 1 if kernel_size % 2 == 0 else kernel_size  # odd taps only
+        self.sample_rate = sample_rate or _default_sample_rate()
+        self.min_low_hz = min_low_hz
+        self.min_band_hz = min_band_hz
+        if out_dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
+        self.out_dtype = out_dtype
+
+        edges_hz = _erb_spaced_edges(out_channels, min_low_hz, self.sample_rate / 2 - min_band_hz)
+        self.low_hz_ = nn.Parameter(torch.Tensor(edges_hz[:-1]).view(-1, 1))
+        self.band_hz_ = nn.Parameter(torch.Tensor(np.diff(edges_hz)).view(-1, 1))
+
+        K = self.kernel_size
+        tap = torch.linspace(0, K - 1, K)
+        # Hamming window over K (not K-1) points, as the reference has it: slightly asymmetric.
+        self.register_buffer("window", 0.54 - 0.46 * torch.cos(2 * math.pi * tap / K))
+        half = (K - 1) / 2.0
+        self.register_buffer("n_", 2 * math.pi * torch.arange(-half, 0).view(1, -1) / self.sample_rate)
+
+    @classmethod
+    def from_reference(cls, ref_module, out_dtype=torch.float32):
+        """Build from an instance of the reference module (or anything with its attributes), copying its
+        parameters and buffers."""
+        m = cls(ref_module.out_channels, ref_module.kernel_size, ref_module.sample_rate,
+                ref_module.min_low_hz, ref_module.min_band_hz, out_dtype=out_dtype)
+        m.load_state_dict({k: v.detach().float() for k, v in ref_module.state_dict().items()})
+        return m.to(ref_module.low_hz_.device)
+
+    def extra_repr(self):
+        return (f"out_channels={self.out_channels}, kernel_size={self.kernel_size}, "
+                f"sample_rate={self.sample_rate}, out_dtype={self.out_dtype}")
+
+    def forward(self, waveform):
+        """waveform (batch, 1, samples) -> (batch, out_channels, samples).  Like the reference's conv1d, a
+        2-D (1, samples) input is read as an unbatched single-channel signal and returns (out_channels, samples)."""
+        unbatched = False
+        if waveform.dim() == 2:
+            if waveform.shape[0] != 1:
+                raise RuntimeError(f"SincConv1d expects (batch, 1, samples); a 2-D input is read as unbatched "
+                                   f"(channels, samples) and needs 1 channel, got {tuple(waveform.shape)}")
+            waveform = waveform.unsqueeze(0)
+            unbatched = True
+        y = SincConvFunction.apply(waveform, self.low_hz_, self.band_hz_, self.window, self.n_,
+                                   self.sample_rate, self.min_low_hz, self.min_band_hz, self.out_dtype)
+        return y.squeeze(0) if unbatched else y
+
+    @torch.no_grad()
+    def filters(self):
+        """The synthesised (out_channels, kernel_size) filter bank, fp32 (debug / inspection)."""
+        lib = _lib.load()
+        dev = self.low_hz_.device
+        if dev.type != "cuda":
+            raise RuntimeError("SincConv1d.filters(): module must be on a CUDA device")
+        low = _small(self.low_hz_, "low_hz_", dev)
+        band = _small(self.band_hz_, "band_hz_", dev)
+        win = _small(self.window, "window", dev)
+        nn_ = _small(self.n_, "n_", dev)
+        out = torch.empty((low.numel(), win.numel()), dtype=torch.float32, device=dev)
+        fb = _bank(low, band, win, nn_, self.sample_rate, self.min_low_hz, self.min_band_hz)
+        with torch.cuda.device(dev):
+            rc = lib.sinc_synthesize(ctypes.byref(fb), _ptr(out),
+                                     ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, "sinc_synthesize")
+        return out
+
+
+def install_into_reference(perception_module, out_dtype=torch.float32):
+    """Swap the class into the reference at its only construction site: ``PerceptionAgent.__init__``
+    resolves the global name ``SincConv1d`` at call time (agents/perception.py:152), so rebinding it
+    before constructing the agent needs no source edit.  Returns the replaced class."""
+    previous = perception_module.SincConv1d
+    if out_dtype is torch.float32:
+        perception_module.SincConv1d = SincConv1d
+    else:
+        class _Bound(SincConv1d):
+            def __init__(self, *a, **k):
+                k.setdefault("out_dtype", out_dtype)
+                super().__init__(*a, **k)
+        _Bound.__name__ = "SincConv1d"
+        perception_module.SincConv1d = _Bound
+    return previous

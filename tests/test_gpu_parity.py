@@ -1,0 +1,273 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and with golden vectors of the reference.
+
+Tolerances (max-norm relative, SURVEY.md section 8c / BASELINE.json north_star):
+  y        <= 1e-5   vs the reference on CPU fp32
+  gx, G    <= 1e-4   vs the reference on CPU fp32
+  d low_hz_, d band_hz_ <= 1e-4 vs the reference evaluated in fp64 (its own fp32 parameter gradients are
+                     round-off noise), plus a conditioning floor for degenerate shapes
+  bf16-output mode: |y - ref| <= 2^-8 |ref| + 1e-3 ||ref||_inf elementwise
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import sinc_oracle as O
+import sincformer_metacog_speech_enhancement_b200 as sb
+from sincformer_metacog_speech_enhancement_b200.sinc import SincConvFunction
+from conftest import golden_case_names, load_golden, max_rel
+
+pytestmark = pytest.mark.gpu
+
+TOL_Y, TOL_GX, TOL_G, TOL_P = 1e-5, 1e-4, 1e-4, 1e-4
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def make_pair(C, K, sr, state=None, out_dtype=torch.float32):
+    orc = O.OracleSincConv1d(C, K, sample_rate=sr)
+    if state is not None:
+        with torch.no_grad():
+            orc.low_hz_.copy_(torch.as_tensor(state["low_hz_"]))
+            orc.band_hz_.copy_(torch.as_tensor(state["band_hz_"]))
+    dut = sb.SincConv1d(C, K, sample_rate=sr, out_dtype=out_dtype)
+    dut.load_state_dict(orc.state_dict())
+    return orc, dut.to(dev())
+
+
+def run_dut(dut, x, g, need_x=True, expose=True):
+    xd = x.to(dev()).clone().requires_grad_(need_x)
+    for p in dut.parameters():
+        p.grad = None
+    SincConvFunction._expose_grad_filters = expose
+    try:
+        y = dut(xd)
+        y.backward(g.to(dev()).to(y.dtype))
+    finally:
+        SincConvFunction._expose_grad_filters = False
+    torch.cuda.synchronize()
+    return dict(y=y.detach().float().cpu(), gx=None if not need_x else xd.grad.cpu(),
+                gfilt=SincConvFunction._last_grad_filters.cpu() if expose else None,
+                g_low=dut.low_hz_.grad.cpu(), g_band=dut.band_hz_.grad.cpu())
+
+
+def param_floor(orc, gfilt64, rel=2e-6):
+    """Conditioning-aware absolute floor for the parameter gradients: what a `rel` relative perturbation of
+    the (C,K) grad-filter does to them (the chain rule is linear in G)."""
+    rng = np.random.default_rng(0)
+    G = np.asarray(gfilt64, dtype=np.float64)
+    noise = rel * np.abs(G).max() * rng.choice([-1.0, 1.0], size=G.shape)
+    dl, db = O.synthesis_vjp(noise, orc.low_hz_, orc.band_hz_, orc.window, orc.n_, orc.sample_rate,
+                             orc.min_low_hz, orc.min_band_hz)
+    return float(np.abs(dl).max()), float(np.abs(db).max())
+
+
+def check_against(orc, out, x, g, tol_y=TOL_Y):
+    o32 = O.full_backward(orc, x, g, torch.float32)
+    o64 = O.full_backward(orc, x, g, torch.float64)
+    assert max_rel(out["y"], o32["y"]) <= tol_y
+    if out["gx"] is not None:
+        assert max_rel(out["gx"], o32["gx"]) <= TOL_GX
+    if out["gfilt"] is not None:
+        assert max_rel(out["gfilt"], o32["gfilt"]) <= TOL_G
+    fl, fb = param_floor(orc, o64["gfilt"].numpy())
+    el = (out["g_low"].double() - o64["g_low"]).abs().max().item()
+    eb = (out["g_band"].double() - o64["g_band"]).abs().max().item()
+    assert el <= TOL_P * o64["g_low"].abs().max().item() + fl, ("g_low", el, o64["g_low"].abs().max().item(), fl)
+    assert eb <= TOL_P * o64["g_band"].abs().max().item() + fb, ("g_band", eb, o64["g_band"].abs().max().item(), fb)
+    return o32, o64
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_golden_vectors_of_the_reference(name):
+    gd = load_golden(name)
+    orc, dut = make_pair(int(gd["C"]), int(gd["K_arg"]), int(gd["sr"]), state=gd)
+    x, g = torch.from_numpy(gd["x"]), torch.from_numpy(gd["g"])
+    out = run_dut(dut, x, g)
+    assert max_rel(out["y"], gd["y"]) <= TOL_Y
+    assert max_rel(out["gx"], gd["gx"]) <= TOL_GX
+    assert max_rel(out["gfilt"], gd["gfilt"]) <= TOL_G
+    o64 = O.full_backward(orc, x, g, torch.float64)
+    fl, fb = param_floor(orc, o64["gfilt"].numpy())
+    assert np.abs(out["g_low"].numpy() - gd["g_low64"]).max() <= TOL_P * np.abs(gd["g_low64"]).max() + fl
+    assert np.abs(out["g_band"].numpy() - gd["g_band64"]).max() <= TOL_P * np.abs(gd["g_band64"]).max() + fb
+    if name.endswith("_edge"):
+        # clamped filter: exactly zero band gradient; zero parameters: exactly zero gradient (sign(0) = 0)
+        assert out["g_band"][40].item() == 0.0 and gd["g_band64"][40] == 0.0
+        assert out["g_low"][7].item() == 0.0 and out["g_band"][11].item() == 0.0
+        assert out["g_band"][50].item() != 0.0       # exactly at the clamp: gradient passes
+
+
+def test_filter_synthesis_matches_reference(init_kat):
+    for key in ("C64_K251_sr8000", "C64_K251_sr16000", "C1_K251_sr8000", "C8_K250_sr8000", "C4_K1_sr8000"):
+        c, k, sr = key.split("_")
+        m = sb.SincConv1d(int(c[1:]), int(k[1:]), sample_rate=int(sr[2:])).to(dev())
+        w = m.filters().cpu()
+        assert max_rel(w, init_kat[f"{key}/filters64"]) <= 2e-7      # fp64 synthesis rounded once to fp32
+        assert max_rel(w, init_kat[f"{key}/filters32"]) <= 1e-5
+
+
+SHAPES = [
+    # C, K, sr, B, T
+    (64, 251, 16000, 2, 1000),
+    (64, 251, 8000, 1, 16000),      # BASELINE cfg 1 shape
+    (64, 251, 16000, 3, 4099),      # ragged T: scalar store / 4-byte copy paths
+    (64, 251, 16000, 2, 513),
+    (64, 251, 8000, 5, 100),        # T < K
+    (64, 251, 8000, 2, 1),
+    (8, 250, 8000, 2, 2048),
+    (70, 31, 44100, 2, 777),        # C not a multiple of 64: two filter blocks
+    (130, 9, 8000, 1, 600),
+    (3, 501, 16000, 2, 1500),       # K > 256: two tap blocks in grad-filter, long-filter synthesis path
+    (4, 1, 8000, 2, 64),
+    (5, 3, 8000, 3, 50),
+]
+
+
+@pytest.mark.parametrize("C,K,sr,B,T", SHAPES)
+def test_forward_backward_vs_oracle(C, K, sr, B, T):
+    orc, dut = make_pair(C, K, sr)
+    gen = torch.Generator().manual_seed(C * 7 + T)
+    with torch.no_grad():
+        orc.low_hz_.mul_(1 + 0.1 * (2 * torch.rand(orc.low_hz_.shape, generator=gen) - 1))
+        orc.band_hz_.mul_(1 + 0.1 * (2 * torch.rand(orc.band_hz_.shape, generator=gen) - 1))
+    dut.load_state_dict(orc.state_dict())
+    x = torch.randn(B, 1, T, generator=gen)
+    g = torch.randn(B, C, T, generator=gen)
+    out = run_dut(dut, x, g)
+    check_against(orc, out, x, g)
+
+
+def test_param_grads_only_like_perception_agent():
+    """Inside PerceptionAgent the waveform does not require grad: only parameter gradients are produced."""
+    orc, dut = make_pair(64, 251, 16000)
+    gen = torch.Generator().manual_seed(5)
+    x, g = torch.randn(2, 1, 3000, generator=gen), torch.randn(2, 64, 3000, generator=gen)
+    out = run_dut(dut, x, g, need_x=False)
+    assert out["gx"] is None
+    check_against(orc, out, x, g)
+
+
+def test_non_contiguous_and_unbatched_inputs():
+    orc, dut = make_pair(16, 33, 8000)
+    gen = torch.Generator().manual_seed(9)
+    big = torch.randn(4, 2, 700, generator=gen)
+    x = big[:, 1:2, :]                       # row stride 1400, still unit time stride
+    assert not x.is_contiguous()
+    y = dut(x.to(dev())[:, :, :]).cpu()
+    assert max_rel(y, orc(x).detach()) <= TOL_Y
+    xt = torch.randn(3, 1, 800, generator=gen)[:, :, ::2]       # time stride 2 -> host makes it contiguous
+    assert max_rel(dut(xt.to(dev())).cpu(), orc(xt).detach()) <= TOL_Y
+    x1 = torch.randn(1, 500, generator=gen)                      # (1,T) is read as unbatched -> (C,T)
+    y1 = dut(x1.to(dev()))
+    assert y1.shape == (16, 500)
+    assert max_rel(y1.cpu(), orc(x1).detach()) <= TOL_Y
+
+
+def test_bf16_output_mode():
+    orc, dut = make_pair(64, 251, 16000, out_dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 1, 4000, generator=gen)
+    g = torch.randn(2, 64, 4000, generator=gen).bfloat16().float()    # grad_out arrives in bf16
+    xd = x.to(dev()).requires_grad_(True)
+    y = dut(xd)
+    assert y.dtype == torch.bfloat16
+    ref = orc(x).detach()
+    err = (y.float().cpu() - ref).abs()
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all())
+    y.backward(g.to(dev()).bfloat16())
+    o32 = O.full_backward(orc, x, g, torch.float32)
+    o64 = O.full_backward(orc, x, g, torch.float64)
+    assert max_rel(xd.grad.cpu(), o32["gx"]) <= TOL_GX
+    fl, fb = param_floor(orc, o64["gfilt"].numpy())
+    assert (dut.low_hz_.grad.cpu().double() - o64["g_low"]).abs().max() <= TOL_P * o64["g_low"].abs().max() + fl
+    assert (dut.band_hz_.grad.cpu().double() - o64["g_band"]).abs().max() <= TOL_P * o64["g_band"].abs().max() + fb
+
+
+def test_bitwise_reproducible():
+    _, dut = make_pair(64, 251, 16000)
+    gen = torch.Generator().manual_seed(3)
+    x, g = torch.randn(4, 1, 9000, generator=gen), torch.randn(4, 64, 9000, generator=gen)
+    a = run_dut(dut, x, g)
+    b = run_dut(dut, x, g)
+    for k in ("y", "gx", "gfilt", "g_low", "g_band"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_under_autocast_stays_fp32():
+    orc, dut = make_pair(8, 31, 8000)
+    x = torch.randn(2, 1, 300, generator=torch.Generator().manual_seed(1))
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = dut(x.to(dev()))
+    assert y.dtype == torch.float32 and max_rel(y.cpu(), orc(x).detach()) <= TOL_Y
+
+
+def test_abi_error_codes_on_device():
+    import ctypes
+    from sincformer_metacog_speech_enhancement_b200 import _lib
+    lib = _lib.load()
+    m = sb.SincConv1d(4, 9).to(dev())
+    fb = _lib.FilterBank()
+    fb.low_hz, fb.band_hz = m.low_hz_.data_ptr(), m.band_hz_.data_ptr()
+    fb.window, fb.n = m.window.data_ptr(), m.n_.data_ptr()
+    fb.C, fb.K, fb.sample_rate, fb.min_low_hz, fb.min_band_hz = 4, 9, 8000.0, 50.0, 50.0
+    x = torch.zeros(1, 1, 16, device=dev())
+    y = torch.zeros(1, 4, 16, device=dev())
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.sinc_forward(ctypes.byref(fb), P(x), 16, P(y), 5, 1, 16, None, 0, None) == -3      # dtype
+    assert lib.sinc_forward(ctypes.byref(fb), P(x), 16, P(y), 0, 0, 16, None, 0, None) == -2      # B = 0
+    g = torch.zeros(1, 4, 16, device=dev())
+    gl = torch.zeros(4, device=dev())
+    assert lib.sinc_backward(ctypes.byref(fb), P(x), 16, P(g), 0, None, P(gl), P(gl), None, 1, 16,
+                             None, 0, None) == -4                                               # workspace
+    assert lib.sinc_forward(ctypes.byref(fb), P(x), 16, P(y), 0, 1, 16, None, 0, None) == 0
+    torch.cuda.synchronize()
+
+
+# ---- full-size, size-independent properties (BASELINE cfg 2: B=32, T=48000) ----------------------------
+def test_full_size_properties():
+    torch.manual_seed(0)
+    B, T, C = 32, 48000, 64
+    dut = sb.SincConv1d(C, 251, sample_rate=16000).to(dev())
+    x1 = torch.randn(B, 1, T, device=dev())
+    x2 = torch.randn(B, 1, T, device=dev())
+    with torch.no_grad():
+        y1, y2 = dut(x1), dut(x2)
+        y12 = dut(2.5 * x1 - x2)
+        assert max_rel(y12, 2.5 * y1 - y2) <= 2e-6                       # linearity in x
+        ys = dut(torch.roll(x1, 7, dims=2))                              # time-shift equivariance (interior)
+        assert max_rel(ys[:, :, 300:-300], torch.roll(y1, 7, dims=2)[:, :, 300:-300]) <= 2e-6
+        del y12, ys, y2
+    # adjoint identity <conv(x), g> == <x, conv^T(g)>  and  <y, g> == sum_ck w[c,k] G[c,k]
+    g = torch.randn(B, C, T, device=dev())
+    xr = x1.clone().requires_grad_(True)
+    SincConvFunction._expose_grad_filters = True
+    try:
+        y = dut(xr)
+        y.backward(g)
+    finally:
+        SincConvFunction._expose_grad_filters = False
+    lhs = (y.detach().double() * g.double()).sum().item()
+    rhs = (xr.grad.double() * x1.double()).sum().item()
+    scale = (y.detach().double().norm() * g.double().norm()).item()
+    assert abs(lhs - rhs) <= 1e-6 * scale
+    G = SincConvFunction._last_grad_filters.double()
+    w = dut.filters().double()
+    assert abs(lhs - (G * w).sum().item()) <= 1e-6 * scale
+    # batch sharding: sum of shard gradients == whole-batch gradient (the multi-GPU exchange is this sum)
+    full_low, full_band = dut.low_hz_.grad.clone(), dut.band_hz_.grad.clone()
+    acc_low, acc_band = torch.zeros_like(full_low), torch.zeros_like(full_band)
+    for r in range(4):
+        b0, b1 = sb.shard_rows(B, r, 4)
+        dut.low_hz_.grad = dut.band_hz_.grad = None
+        dut(x1[b0:b1]).backward(g[b0:b1])
+        acc_low += dut.low_hz_.grad
+        acc_band += dut.band_hz_.grad
+    assert max_rel(acc_low, full_low) <= 1e-4 and max_rel(acc_band, full_band) <= 1e-4
+    # a row of the full-size result against the oracle
+    orc = O.OracleSincConv1d(C, 251, sample_rate=16000)
+    assert max_rel(y[5].detach().cpu(), orc(x1[5:6].cpu()).detach()[0]) <= TOL_Y
