@@ -111,6 +111,15 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
                   float* grad_filters, int64_t B, int64_t T, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Diagnostic: run `ksteps` tcgen05.mma (kind::tf32, M = 128) on caller-supplied shared-memory images and
+ * raw matrix / instruction descriptors and return the 128 x N accumulator.  Not part of the replacement
+ * surface (the reference has no counterpart); it exists so the operand layouts the tensor-core engine
+ * relies on -- in-place Toeplitz descriptors over the waveform tile, TMEM-resident filter operand -- are
+ * pinned by a hardware test (tests/test_gpu_tc_probe.py).  *status_out: 0 ok, 1 the MMA never completed. */
+int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int bytesB, unsigned long long descA,
+                  unsigned long long descB, unsigned int idesc, int ksteps, int a_step, int b_step,
+                  int a_from_tmem, int a_cols, int N, float* D_out, int* status_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -503,7 +503,8 @@ __global__ void __launch_bounds__(BI_THREADS, 1) bwd_input_fma_kernel(const BwdI
 // =================================================================================================
 // finalize: fixed-order fp64 reduction of the partial tiles + synthesis chain rule
 // =================================================================================================
-constexpr int FN_THREADS = 256;
+constexpr int FN_THREADS = 1024;
+constexpr int FN_SPLIT = 4;  // slot quarters summed in parallel, combined in fixed order
 
 __device__ __forceinline__ double block_sum(double v, double* scratch) {
   v = warp_sum(v);
@@ -524,16 +525,28 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
                                                               float* grad_band, float* grad_filters) {
   extern __shared__ __align__(16) double dsm[];
   const int K = bank.K, H = (K - 1) / 2;
-  double* Gs = dsm;          // [K] reduced grad-filter
-  double* us = dsm + K;      // [K] un-normalised taps u
-  double* scratch = us + K;  // [8]
+  double* Gs = dsm;                  // [K] reduced grad-filter
+  double* us = dsm + K;              // [K] un-normalised taps u
+  double* scratch = us + K;          // [32]
+  double* part = scratch + 32;       // [FN_SPLIT][K]
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
 
+  {
+    const int q = tid / (FN_THREADS / FN_SPLIT), kk = tid % (FN_THREADS / FN_SPLIT);
+    for (int k = kk; k < K; k += FN_THREADS / FN_SPLIT) {
+      double s = 0.0;
+      const float* p = partials + (size_t)c * Kpad + k;
+#pragma unroll 4
+      for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * Cpad * Kpad);
+      part[q * K + k] = s;
+    }
+  }
+  __syncthreads();
   for (int k = tid; k < K; k += FN_THREADS) {
     double s = 0.0;
-    const float* p = partials + (size_t)c * Kpad + k;
-    for (int sl = 0; sl < slots; ++sl) s += (double)p[(size_t)sl * Cpad * Kpad];
+#pragma unroll
+    for (int q = 0; q < FN_SPLIT; ++q) s += part[q * K + k];
     Gs[k] = s;
     if (grad_filters) grad_filters[(size_t)c * K + k] = (float)s;
   }
@@ -734,7 +747,7 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
 
 cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad,
                             float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st) {
-  const size_t smem = (size_t)(2 * bank.K + 16) * sizeof(double);
+  const size_t smem = (size_t)((2 + FN_SPLIT) * bank.K + 32) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e =
         cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

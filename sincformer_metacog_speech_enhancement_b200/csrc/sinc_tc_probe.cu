@@ -1,0 +1,127 @@
+// Hardware probe for the tcgen05 operand layouts the tensor-core engine relies on (diagnostic entry point
+// sinc_tc_probe, used by tests/test_gpu_tc_probe.py).  The host supplies raw shared-memory images, raw
+// matrix descriptors (without the start address) and the instruction descriptor; the kernel runs `ksteps`
+// MMAs into one accumulator and returns D[128][N].  This is how the in-place Toeplitz descriptors
+// (overlapping core matrices, LBO = 16 B) and the TMEM A-operand layout were validated on B200.
+#include "sinc_internal.h"
+#include "sinc_tc.cuh"
+
+namespace sinc {
+
+struct ProbeArgs {
+  const uint8_t* imgA;   // smem image of A, or (a_from_tmem) row-major float [128][a_cols]
+  const uint8_t* imgB;
+  int bytesA, bytesB;
+  unsigned long long descA, descB;  // start-address field zero
+  uint32_t idesc;
+  int ksteps;
+  int a_step;  // bytes per k-step (smem A) or TMEM columns per k-step
+  int b_step;  // bytes per k-step
+  int a_from_tmem, a_cols;
+  int N;
+  float* D;    // [128][N]
+  int* status; // 0 ok, 1 = mbarrier wait timed out
+};
+
+__global__ void __launch_bounds__(128, 1) tc_probe_kernel(const ProbeArgs a) {
+  extern __shared__ __align__(1024) uint8_t psm[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* sA = psm;
+  uint8_t* sB = psm + ((a.a_from_tmem ? 0 : a.bytesA) + 1023) / 1024 * 1024;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (!a.a_from_tmem)
+    for (int i = tid; i < a.bytesA / 4; i += 128) reinterpret_cast<uint32_t*>(sA)[i] = reinterpret_cast<const uint32_t*>(a.imgA)[i];
+  for (int i = tid; i < a.bytesB / 4; i += 128) reinterpret_cast<uint32_t*>(sB)[i] = reinterpret_cast<const uint32_t*>(a.imgB)[i];
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc(&tmem_base_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+  const uint32_t a_col0 = 256;
+  if (a.a_from_tmem) {
+    const float* row = reinterpret_cast<const float*>(a.imgA) + (size_t)tid * a.a_cols;
+    for (int c = 0; c < a.a_cols; c += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __float_as_uint(row[c + i]);
+      tc::tmem_st8(tmem + lane_base + a_col0 + c, v);
+    }
+    tc::tmem_st_wait();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+  }
+  if (tid == 0) {
+    for (int s = 0; s < a.ksteps; ++s) {
+      const uint64_t bd = tc::desc_at(a.descB, tc::smem_addr(sB) + s * a.b_step);
+      if (a.a_from_tmem)
+        tc::mma_tf32_ts(tmem, tmem + a_col0 + s * a.a_step, bd, a.idesc, s > 0);
+      else
+        tc::mma_tf32_ss(tmem, tc::desc_at(a.descA, tc::smem_addr(sA) + s * a.a_step), bd, a.idesc, s > 0);
+    }
+    tc::mma_commit(&bar);
+  }
+  const bool ok = tc::mbar_wait(&bar, 0);
+  tc::fence_after_sync();
+  if (!ok && tid == 0) *a.status = 1;
+  if (ok) {
+    for (int n0 = 0; n0 < a.N; n0 += 8) {
+      uint32_t v[8];
+      tc::tmem_ld8(tmem + lane_base + n0, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a.D[(size_t)tid * a.N + n0 + i] = __uint_as_float(v[i]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+}  // namespace sinc
+
+extern "C" int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int bytesB, unsigned long long descA,
+                             unsigned long long descB, unsigned int idesc, int ksteps, int a_step, int b_step,
+                             int a_from_tmem, int a_cols, int N, float* D_out, int* status, void* stream) {
+  using namespace sinc;
+  if (!imgA || !imgB || !D_out || !status) return SINC_E_NULL;
+  if (N < 8 || N > 256 || (N % 8) || ksteps < 1 || bytesA < 0 || bytesB < 0 || (bytesA % 4) || (bytesB % 4)) return SINC_E_SHAPE;
+  if (a_from_tmem && (a_cols % 8 || a_cols > 256)) return SINC_E_SHAPE;
+  DeviceInfo di;
+  int r = get_device_info(&di);
+  if (r) return r;
+  if (di.cc_major != 10) return SINC_E_DEVICE;
+  ProbeArgs a;
+  a.imgA = (const uint8_t*)imgA;
+  a.imgB = (const uint8_t*)imgB;
+  a.bytesA = bytesA;
+  a.bytesB = bytesB;
+  a.descA = descA;
+  a.descB = descB;
+  a.idesc = idesc;
+  a.ksteps = ksteps;
+  a.a_step = a_step;
+  a.b_step = b_step;
+  a.a_from_tmem = a_from_tmem;
+  a.a_cols = a_cols;
+  a.N = N;
+  a.D = D_out;
+  a.status = status;
+  const size_t smem = ((a_from_tmem ? 0 : bytesA) + 1023) / 1024 * 1024 + (bytesB + 1023) / 1024 * 1024 + 1024;
+  if (smem > (size_t)di.max_smem_optin) return SINC_E_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return (int)cudaGetLastError();
+}

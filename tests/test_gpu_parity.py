@@ -6,6 +6,14 @@ Tolerances (max-norm relative, SURVEY.md section 8c / BASELINE.json north_star):
   d low_hz_, d band_hz_ <= 1e-4 vs the reference evaluated in fp64 (its own fp32 parameter gradients are
                      round-off noise), plus a conditioning floor for degenerate shapes
   bf16-output mode: |y - ref| <= 2^-8 |ref| + 1e-3 ||ref||_inf elementwise
+
+The fp32 reference is itself only ~2e-6 (init parameters) to 2.3e-5 (the `edge` golden case: a 50 Hz band at
+16 kHz cancels harder) away from its own fp64 evaluation, because it synthesises the filters in fp32.  The CUDA
+path synthesises in fp64, so the y gate is applied as
+    ||y - y_ref32|| <= 1e-5 + ||y_ref32 - y_ref64||      (the reference's own round-off is not ours to match)
+    ||y - y_ref64|| <= 1e-5                               (always)
+both relative to ||y_ref||_inf.  With the reference's gap below 1e-5 (all init/perturbed cases) the first line
+is the plain 1e-5 gate against the fp32 reference.
 """
 import copy
 
@@ -69,7 +77,9 @@ def param_floor(orc, gfilt64, rel=2e-6):
 def check_against(orc, out, x, g, tol_y=TOL_Y):
     o32 = O.full_backward(orc, x, g, torch.float32)
     o64 = O.full_backward(orc, x, g, torch.float64)
-    assert max_rel(out["y"], o32["y"]) <= tol_y
+    ref_gap = max_rel(o32["y"], o64["y"])
+    assert max_rel(out["y"], o64["y"]) <= tol_y
+    assert max_rel(out["y"], o32["y"]) <= tol_y + (ref_gap if ref_gap > 0.5 * tol_y else 0.0)
     if out["gx"] is not None:
         assert max_rel(out["gx"], o32["gx"]) <= TOL_GX
     if out["gfilt"] is not None:
@@ -88,10 +98,12 @@ def test_golden_vectors_of_the_reference(name):
     orc, dut = make_pair(int(gd["C"]), int(gd["K_arg"]), int(gd["sr"]), state=gd)
     x, g = torch.from_numpy(gd["x"]), torch.from_numpy(gd["g"])
     out = run_dut(dut, x, g)
-    assert max_rel(out["y"], gd["y"]) <= TOL_Y
+    o64 = O.full_backward(orc, x, g, torch.float64)
+    ref_gap = float(gd["y32_vs_y64"])            # the reference's own fp32-vs-fp64 distance, stored with the vector
+    assert max_rel(out["y"], o64["y"]) <= TOL_Y
+    assert max_rel(out["y"], gd["y"]) <= TOL_Y + (ref_gap if ref_gap > 0.5 * TOL_Y else 0.0)
     assert max_rel(out["gx"], gd["gx"]) <= TOL_GX
     assert max_rel(out["gfilt"], gd["gfilt"]) <= TOL_G
-    o64 = O.full_backward(orc, x, g, torch.float64)
     fl, fb = param_floor(orc, o64["gfilt"].numpy())
     assert np.abs(out["g_low"].numpy() - gd["g_low64"]).max() <= TOL_P * np.abs(gd["g_low64"]).max() + fl
     assert np.abs(out["g_band"].numpy() - gd["g_band64"]).max() <= TOL_P * np.abs(gd["g_band64"]).max() + fb

@@ -1,0 +1,129 @@
+"""Hardware probe of tcgen05 operand layouts (run on the B200 box):  python tools/tc_probe.py [case ...]
+Each case runs in its own subprocess (a faulting descriptor must not take the others down)."""
+import ctypes
+import json
+import subprocess
+import sys
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+
+def smem_desc(lbo, sbo):
+    return ((lbo >> 4) & 0x3FFF) << 16 | ((sbo >> 4) & 0x3FFF) << 32 | 1 << 46
+
+
+def idesc(M, N, a_mn, b_mn):
+    return (1 << 4) | (2 << 7) | (2 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def kmajor_image(mat, lbo, sbo):
+    """mat [rows][K] fp32 -> canonical no-swizzle K-major image: addr(r,kc) = (r%8)*16 + (r//8)*sbo + kc*lbo."""
+    rows, K = mat.shape
+    size = (rows // 8 - 1) * sbo + (K // 4 - 1) * lbo + 128
+    img = np.zeros(size // 4, dtype=np.float32)
+    for r in range(rows):
+        for kc in range(K // 4):
+            a = ((r % 8) * 16 + (r // 8) * sbo + kc * lbo) // 4
+            img[a:a + 4] = mat[r, 4 * kc:4 * kc + 4]
+    return img
+
+
+def run(case):
+    import torch
+    from sincformer_metacog_speech_enhancement_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    M = 128
+    ri = lambda *s: rng.integers(-4, 5, size=s).astype(np.float32)
+    a_from_tmem, a_cols = 0, 0
+    if case in ("kmajor_ss", "kmajor_ss_swapped"):
+        N, ks = 64, 3
+        A, B = ri(M, 8 * ks), ri(N, 8 * ks)
+        lbo, sbo = 128, 128 * (8 * ks // 4)
+        if case.endswith("swapped"):
+            imgA, imgB = kmajor_image(A, lbo, sbo), kmajor_image(B, lbo, sbo)
+            dA = dB = smem_desc(sbo, lbo)
+        else:
+            imgA, imgB = kmajor_image(A, lbo, sbo), kmajor_image(B, lbo, sbo)
+            dA = dB = smem_desc(lbo, sbo)
+        a_step = b_step = 256
+        idc = idesc(M, N, 0, 0)
+        expect = A @ B.T
+    elif case in ("toeplitz_b", "toeplitz_b_n128", "toeplitz_b_n256"):
+        N = {"toeplitz_b": 64, "toeplitz_b_n128": 128, "toeplitz_b_n256": 256}[case]
+        ks = 4
+        A = ri(M, 8 * ks)
+        x = ri(4 * N + 8 * ks + 8)
+        Bm = np.stack([x[4 * n:4 * n + 8 * ks] for n in range(N)])       # B[n,k] = x[4n+k]
+        lbo, sbo = 128, 128 * (8 * ks // 4)
+        imgA, dA, a_step = kmajor_image(A, lbo, sbo), smem_desc(lbo, sbo), 256
+        imgB, dB, b_step = x.copy(), smem_desc(16, 128), 32
+        idc = idesc(M, N, 0, 0)
+        expect = A @ Bm.T
+    elif case == "tmem_a_toeplitz_b":
+        N, ks = 128, 4
+        A = ri(M, 8 * ks)
+        x = ri(4 * N + 8 * ks + 8)
+        Bm = np.stack([x[4 * n:4 * n + 8 * ks] for n in range(N)])
+        imgA, dA, a_step = A.copy(), 0, 8
+        a_from_tmem, a_cols = 1, 8 * ks
+        imgB, dB, b_step = x.copy(), smem_desc(16, 128), 32
+        idc = idesc(M, N, 0, 0)
+        expect = A @ Bm.T
+    elif case in ("mnmajor_gradfilter", "mnmajor_gradfilter_n256"):
+        # D[(c,r), k'] = sum_j g[c, 4j+r] * x[4j+k'];  A MN-major straight from a g tile, B MN-major Toeplitz
+        N = 64 if case == "mnmajor_gradfilter" else 256
+        ks = 3                                  # 8 j's (32 samples) per step
+        P = 32 * ks + 8                         # g tile row pitch in floats (multiple of 4)
+        g = ri(32, P)
+        x = ri(32 * ks + N + 8)
+        Am = np.zeros((M, 8 * ks), np.float32)
+        for c in range(32):
+            for r in range(4):
+                Am[4 * c + r] = g[c, r:r + 32 * ks:4]
+        Bm = np.stack([x[kp:kp + 32 * ks:4] for kp in range(N)])         # B[k', j] = x[4j + k']
+        imgA, dA, a_step = g.reshape(-1).copy(), smem_desc(128, 4 * P), 128
+        imgB, dB, b_step = x.copy(), smem_desc(128, 16), 128
+        idc = idesc(M, N, 1, 1)
+        expect = Am @ Bm.T
+    else:
+        raise SystemExit(f"unknown case {case}")
+    dev = torch.device("cuda:0")
+    tA = torch.from_numpy(np.ascontiguousarray(imgA)).to(dev)
+    tB = torch.from_numpy(np.ascontiguousarray(imgB)).to(dev)
+    D = torch.full((M, N), -777.0, device=dev)
+    st = torch.zeros(1, dtype=torch.int32, device=dev)
+    rc = lib.sinc_tc_probe(ctypes.c_void_p(tA.data_ptr()), tA.numel() * 4, ctypes.c_void_p(tB.data_ptr()), tB.numel() * 4,
+                           dA, dB, idc, ks, a_step, b_step, a_from_tmem, a_cols, N, ctypes.c_void_p(D.data_ptr()),
+                           ctypes.c_void_p(st.data_ptr()), None)
+    torch.cuda.synchronize()
+    got = D.cpu().numpy()
+    bad = int((got != expect).sum())
+    res = {"case": case, "rc": rc, "status": int(st.item()), "mismatches": bad, "total": int(expect.size),
+           "max_abs_err": float(np.abs(got - expect).max())}
+    if bad:
+        rows = np.unique(np.argwhere(got != expect)[:, 0])
+        cols = np.unique(np.argwhere(got != expect)[:, 1])
+        res["bad_rows"] = rows[:16].tolist()
+        res["bad_cols"] = cols[:16].tolist()
+        res["got00"] = got[:2, :4].tolist()
+        res["exp00"] = expect[:2, :4].tolist()
+    print(json.dumps(res))
+    return res
+
+
+ALL = ["kmajor_ss", "kmajor_ss_swapped", "toeplitz_b", "toeplitz_b_n128", "toeplitz_b_n256", "tmem_a_toeplitz_b",
+       "mnmajor_gradfilter", "mnmajor_gradfilter_n256"]
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--one":
+        run(sys.argv[2])
+    else:
+        for c in (sys.argv[1:] or ALL):
+            p = subprocess.run([sys.executable, __file__, "--one", c], capture_output=True, text=True, timeout=120)
+            out = [l for l in p.stdout.splitlines() if l.startswith("{")]
+            print(out[-1] if out else json.dumps({"case": c, "crashed": p.returncode, "stderr": p.stderr[-400:]}), flush=True)
