@@ -111,6 +111,10 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
                   float* grad_filters, int64_t B, int64_t T, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Diagnostic: *status_host = 1 if any tcgen05 kernel of this process gave up waiting on one of its internal
+ * barriers (a protocol bug; results are then invalid).  Synchronises the device. */
+int sinc_tc_status(int* status_host);
+
 /* Diagnostic: run `ksteps` tcgen05.mma (kind::tf32, M = 128) on caller-supplied shared-memory images and
  * raw matrix / instruction descriptors and return the 128 x N accumulator.  Not part of the replacement
  * surface (the reference has no counterpart); it exists so the operand layouts the tensor-core engine

@@ -49,7 +49,7 @@ def set_params(m, mode, seed):
             m.low_hz_[7] = 0.0                    # sign(0) = 0
             m.band_hz_[11] = 0.0
             m.band_hz_[20] = -m.band_hz_[20]
-            m.band_hz_[40] = 5000.0               # clamped at Nyquist -> zero band gradient
+            m.band_hz_[40] = 1.0e5               # clamped at Nyquist -> zero band gradient
             # exactly at the clamp boundary: low + min_band + |band| == sr/2 passes the gradient
             lowv = m.min_low_hz + m.low_hz_[50].abs()
             m.band_hz_[50] = m.sample_rate / 2.0 - lowv - m.min_band_hz

@@ -19,7 +19,7 @@ ENGINE_AUTO, ENGINE_FMA, ENGINE_TC = 0, 1, 2
 ABI_SYMBOLS = (
     "sinc_abi_version", "sinc_strerror", "sinc_kernel_launch_count", "sinc_set_engine",
     "sinc_get_engine", "sinc_last_engine_mask", "sinc_workspace_bytes", "sinc_synthesize",
-    "sinc_forward", "sinc_backward", "sinc_tc_probe",
+    "sinc_forward", "sinc_backward", "sinc_tc_probe", "sinc_tc_status",
 )
 
 
@@ -67,8 +67,8 @@ def _declare(lib):
     lib.sinc_backward.argtypes = [c.POINTER(FilterBank), c.c_void_p, c.c_int64, c.c_void_p, c.c_int32,
                                   c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
                                   c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p]
-
-
+    lib.sinc_tc_status.restype = c.c_int
+    lib.sinc_tc_status.argtypes = [c.POINTER(c.c_int)]
     lib.sinc_tc_probe.restype = c.c_int
     lib.sinc_tc_probe.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_int, c.c_ulonglong, c.c_ulonglong, c.c_uint,
                                   c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p,

@@ -10,6 +10,8 @@ namespace sinc {
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
 static thread_local int t_last_mask = 0;
+// AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
+constexpr bool kAutoPrefersTcForward = false;
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -94,6 +96,11 @@ int sinc_set_engine(int engine) {
 int sinc_get_engine(void) { return g_engine.load(); }
 int sinc_last_engine_mask(void) { return t_last_mask; }
 
+int sinc_tc_status(int* status_host) {
+  if (!status_host) return SINC_E_NULL;
+  return read_tc_status(status_host);
+}
+
 size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K) {
   (void)B;
   (void)T;
@@ -126,11 +133,18 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   if ((r = check_device(&di))) return r;
   const Bank bank = to_bank(fb);
   const int engine = g_engine.load();
-  if (engine == SINC_ENGINE_TC) return SINC_E_ENGINE;  // tcgen05 forward: see sinc_tc.cu (not built yet)
-  if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
-  cudaError_t e = launch_fwd_fma(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
+  const bool tc_ok = tc_fwd_supported(bank.C, bank.K, T, y, y_dtype, di);
+  if (engine == SINC_ENGINE_TC && !tc_ok) return SINC_E_ENGINE;
+  const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcForward));
+  cudaError_t e;
+  if (use_tc) {
+    e = launch_fwd_tc(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
+  } else {
+    if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
+    e = launch_fwd_fma(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
+  }
   if (e != cudaSuccess) return (int)e;
-  t_last_mask = (t_last_mask & ~1);
+  t_last_mask = (t_last_mask & ~1) | (use_tc ? 1 : 0);
   return 0;
 }
 
@@ -149,8 +163,6 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   DeviceInfo di;
   if ((r = check_device(&di))) return r;
   const Bank bank = to_bank(fb);
-  const int engine = g_engine.load();
-  if (engine == SINC_ENGINE_TC) return SINC_E_ENGINE;
   if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;

@@ -78,4 +78,10 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
 cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad,
                             float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st);
 
+// ---- tcgen05 engine (sinc_tc_fwd.cu, ...) -------------------------------------------------------------
+bool tc_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di);
+cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
+                          const DeviceInfo& di, cudaStream_t st);
+int read_tc_status(int* out);
+
 }  // namespace sinc

@@ -1,0 +1,103 @@
+"""The tcgen05 (tensor-core) engine: operand-layout probes on hardware and parity of the TC kernels with the
+oracle, at the same tolerances as the FMA engine (tests/test_gpu_parity.py)."""
+import ctypes
+import os
+import subprocess
+import sys
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import sinc_oracle as O
+import sincformer_metacog_speech_enhancement_b200 as sb
+from sincformer_metacog_speech_enhancement_b200 import _lib
+from conftest import ROOT, max_rel
+from test_gpu_parity import make_pair, run_dut, check_against, dev, TOL_Y
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def tc_engine():
+    sb.set_engine("tc")
+    yield
+    sb.set_engine("auto")
+
+
+def tc_status():
+    v = ctypes.c_int(-1)
+    _lib.check(_lib.load().sinc_tc_status(ctypes.byref(v)), "sinc_tc_status")
+    return v.value
+
+
+@pytest.mark.parametrize("case", ["kmajor_ss", "toeplitz_b", "toeplitz_b_n128", "toeplitz_b_n256", "tmem_a_toeplitz_b"])
+def test_operand_layout_probe(case):
+    """In-place Toeplitz B descriptors (overlapping core matrices) and the TMEM A operand, bit-exact on
+    integer-valued data (tools/tc_probe.py)."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tc_probe.py"), "--one", case],
+                       capture_output=True, text=True, timeout=300)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    assert lines, p.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert res["rc"] == 0 and res["status"] == 0 and res["mismatches"] == 0, res
+
+
+TC_FWD_SHAPES = [
+    (64, 251, 16000, 2, 1000),
+    (64, 251, 8000, 1, 16000),      # BASELINE cfg 1
+    (64, 251, 16000, 3, 4100),      # last tile of each row is partial
+    (64, 251, 8000, 5, 100),        # T < K
+    (64, 251, 8000, 2, 4),
+    (8, 250, 8000, 2, 2048),
+    (70, 31, 44100, 2, 776),        # 3 filter blocks, the last one ragged
+    (130, 9, 8000, 1, 600),
+    (32, 253, 16000, 2, 1536),      # largest K the 256-deep GEMM holds
+    (4, 1, 8000, 2, 64),
+    (5, 3, 8000, 3, 52),
+]
+
+
+@pytest.mark.parametrize("C,K,sr,B,T", TC_FWD_SHAPES)
+def test_tc_forward_vs_oracle(tc_engine, C, K, sr, B, T):
+    orc, dut = make_pair(C, K, sr)
+    gen = torch.Generator().manual_seed(C * 11 + T)
+    with torch.no_grad():
+        orc.low_hz_.mul_(1 + 0.1 * (2 * torch.rand(orc.low_hz_.shape, generator=gen) - 1))
+        orc.band_hz_.mul_(1 + 0.1 * (2 * torch.rand(orc.band_hz_.shape, generator=gen) - 1))
+    dut.load_state_dict(orc.state_dict())
+    x = torch.randn(B, 1, T, generator=gen)
+    with torch.no_grad():
+        y = dut(x.to(dev()))
+    torch.cuda.synchronize()
+    assert _lib.load().sinc_last_engine_mask() & 1, "forward did not run on the tcgen05 engine"
+    assert tc_status() == 0
+    y32 = orc(x).detach()
+    y64 = O.full_backward(orc, x, torch.zeros(B, C, T), torch.float64)["y"]
+    gap = max_rel(y32, y64)
+    assert max_rel(y.cpu(), y64) <= TOL_Y
+    assert max_rel(y.cpu(), y32) <= TOL_Y + (gap if gap > 0.5 * TOL_Y else 0.0)
+
+
+def test_tc_forward_full_size_matches_fma_engine(tc_engine):
+    torch.manual_seed(0)
+    dut = sb.SincConv1d(64, 251, sample_rate=16000).to(dev())
+    x = torch.randn(32, 1, 48000, device=dev())
+    with torch.no_grad():
+        y_tc = dut(x)
+        sb.set_engine("fma")
+        y_fma = dut(x)
+    assert tc_status() == 0
+    assert max_rel(y_tc, y_fma) <= 2e-6
+    orc = O.OracleSincConv1d(64, 251, sample_rate=16000)
+    assert max_rel(y_tc[31].cpu(), orc(x[31:32].cpu()).detach()[0]) <= TOL_Y
+
+
+def test_tc_engine_refuses_unsupported_shapes(tc_engine):
+    dut = sb.SincConv1d(8, 31, sample_rate=8000).to(dev())
+    with pytest.raises(RuntimeError, match="engine"):
+        dut(torch.randn(1, 1, 4099, device=dev()))          # T % 4 != 0: rows are not 16-byte aligned
+    big = sb.SincConv1d(4, 301, sample_rate=8000).to(dev())
+    with pytest.raises(RuntimeError, match="engine"):
+        big(torch.randn(1, 1, 1024, device=dev()))          # K + 3 > 256
