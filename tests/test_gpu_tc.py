@@ -89,7 +89,7 @@ def test_tc_forward_full_size_matches_fma_engine(tc_engine):
         sb.set_engine("fma")
         y_fma = dut(x)
     assert tc_status() == 0
-    assert max_rel(y_tc, y_fma) <= 2e-6
+    assert max_rel(y_tc, y_fma) <= 5e-6        # two independent fp32-grade evaluations (~2e-6 each vs exact)
     orc = O.OracleSincConv1d(64, 251, sample_rate=16000)
     assert max_rel(y_tc[31].cpu(), orc(x[31:32].cpu()).detach()[0]) <= TOL_Y
 

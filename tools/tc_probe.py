@@ -90,6 +90,51 @@ def run(case):
         imgB, dB, b_step = x.copy(), smem_desc(128, 16), 128
         idc = idesc(M, N, 1, 1)
         expect = Am @ Bm.T
+    elif case.startswith("mn_"):
+        # isolate MN-major semantics: one operand MN-major, the other canonical K-major
+        N, ks = 64, 3
+        Kt = 8 * ks
+        lbo, sbo = 128, 128 * (Kt // 4)
+        A, Bmat = ri(M, Kt), ri(N, Kt)
+        imgA, dA, a_step, a_mn = kmajor_image(A, lbo, sbo), smem_desc(lbo, sbo), 256, 0
+        imgB, dB, b_step, b_mn = kmajor_image(Bmat, lbo, sbo), smem_desc(lbo, sbo), 256, 0
+
+        def mn_dense(mat):
+            """[rows][Kt] -> MN-major dense image: per k-step block of (rows/4) chunks x 8 k-rows x 16 B."""
+            rows = mat.shape[0]
+            img = np.zeros(ks * (rows // 4) * 32, np.float32)
+            for s_ in range(ks):
+                for i in range(rows // 4):
+                    for kr in range(8):
+                        a = (s_ * (rows // 4) * 128 + i * 128 + kr * 16) // 4
+                        img[a:a + 4] = mat[4 * i:4 * i + 4, 8 * s_ + kr]
+            return img, (rows // 4) * 128
+        if case in ("mn_a_dense", "mn_a_dense_swap"):
+            imgA, a_step = mn_dense(A)
+            dA = smem_desc(128, 128) if case == "mn_a_dense" else smem_desc(128, 128)
+            a_mn = 1
+        elif case == "mn_b_dense":
+            imgB, b_step = mn_dense(Bmat)
+            dB, b_mn = smem_desc(128, 128), 1
+        elif case == "mn_a_gtile":
+            P = 32 * ks + 8
+            g = ri(32, P)
+            for c in range(32):
+                for r in range(4):
+                    A[4 * c + r] = g[c, r:r + 32 * ks:4]
+            imgA, dA, a_step, a_mn = g.reshape(-1).copy(), smem_desc(128, 4 * P), 128, 1
+        elif case == "mn_b_toeplitz":
+            x = ri(32 * ks + N + 8)
+            Bmat = np.stack([x[kp:kp + 32 * ks:4] for kp in range(N)])
+            imgB, dB, b_step, b_mn = x.copy(), smem_desc(128, 16), 128, 1
+        elif case == "mn_b_toeplitz_lbo16":
+            x = ri(32 * ks + N + 8)
+            Bmat = np.stack([x[kp:kp + 32 * ks:4] for kp in range(N)])
+            imgB, dB, b_step, b_mn = x.copy(), smem_desc(16, 16), 128, 1
+        else:
+            raise SystemExit(f"unknown case {case}")
+        idc = idesc(M, N, a_mn, b_mn)
+        expect = A @ Bmat.T
     else:
         raise SystemExit(f"unknown case {case}")
     dev = torch.device("cuda:0")
@@ -117,7 +162,8 @@ def run(case):
 
 
 ALL = ["kmajor_ss", "kmajor_ss_swapped", "toeplitz_b", "toeplitz_b_n128", "toeplitz_b_n256", "tmem_a_toeplitz_b",
-       "mnmajor_gradfilter", "mnmajor_gradfilter_n256"]
+       "mnmajor_gradfilter", "mnmajor_gradfilter_n256", "mn_a_dense", "mn_b_dense", "mn_a_gtile", "mn_b_toeplitz",
+       "mn_b_toeplitz_lbo16"]
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
