@@ -12,6 +12,7 @@ static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
 static thread_local int t_last_mask = 0;
 // AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
 constexpr bool kAutoPrefersTcForward = true;  // parity-green on B200 (tests/test_gpu_tc.py, r01c)
+constexpr bool kAutoPrefersTcBwdFilter = false;
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -43,6 +44,8 @@ WorkspaceLayout workspace_layout(int C, int K) {
   wl.Cpad = round_up(C, kChanBlock);
   wl.Kpad = round_up(K, kTapBlock);
   wl.partial_bytes = (size_t)kMaxPartialSlots * wl.Cpad * wl.Kpad * sizeof(float);
+  const size_t tc_bytes = tc_bwd_filter_partial_bytes(C);
+  if (tc_bytes > wl.partial_bytes) wl.partial_bytes = tc_bytes;
   wl.total_bytes = (wl.partial_bytes + 255) / 256 * 256 + 256;
   return wl;
 }
@@ -166,6 +169,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
+  int mask = 0;
   if (grad_x) {
     e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
     if (e != cudaSuccess) return (int)e;
@@ -175,12 +179,19 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     if (!workspace || workspace_bytes < wl.total_bytes) return SINC_E_WORKSPACE;
     float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
     int slots = 0;
-    e = launch_bwd_filter_fma(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
+    const int engine = g_engine.load();
+    const bool tc_ok = tc_bwd_filter_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
+    const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter));
+    if (use_tc)
+      e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
+    else
+      e = launch_bwd_filter_fma(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
     if (e != cudaSuccess) return (int)e;
-    e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, grad_low, grad_band, grad_filters, st);
+    e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, use_tc ? 1 : 0, grad_low, grad_band, grad_filters, st);
     if (e != cudaSuccess) return (int)e;
+    mask |= use_tc ? 4 : 0;
   }
-  t_last_mask = (t_last_mask & 1);
+  t_last_mask = (t_last_mask & 1) | mask;
   return 0;
 }
 

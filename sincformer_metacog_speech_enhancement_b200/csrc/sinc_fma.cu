@@ -520,9 +520,12 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 
 __device__ __forceinline__ double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 
+// layout 0: FMA partial tiles [slot][Cpad][Kpad];  layout 1: tcgen05 partial tiles [slot][nblk][128][320] with
+// row (c_local, h) and column rho*80 + n holding tap k = 4n + rho - 8h (sinc_tc_bwd_filter.cu)
 __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, const float* __restrict__ partials,
-                                                              int slots, int Cpad, int Kpad, float* grad_low,
-                                                              float* grad_band, float* grad_filters) {
+                                                              int slots, int Cpad, int Kpad, int layout,
+                                                              float* grad_low, float* grad_band,
+                                                              float* grad_filters) {
   extern __shared__ __align__(16) double dsm[];
   const int K = bank.K, H = (K - 1) / 2;
   double* Gs = dsm;                  // [K] reduced grad-filter
@@ -536,9 +539,20 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
     const int q = tid / (FN_THREADS / FN_SPLIT), kk = tid % (FN_THREADS / FN_SPLIT);
     for (int k = kk; k < K; k += FN_THREADS / FN_SPLIT) {
       double s = 0.0;
-      const float* p = partials + (size_t)c * Kpad + k;
+      if (layout == 0) {
+        const float* p = partials + (size_t)c * Kpad + k;
 #pragma unroll 4
-      for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * Cpad * Kpad);
+        for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * Cpad * Kpad);
+      } else {
+        const int nblk = Cpad / 64;
+        const size_t slot_stride = (size_t)nblk * 128 * 320;
+        const float* p0 = partials + ((size_t)(c / 64) * 128 + 2 * (c % 64)) * 320 + (k & 3) * 80;
+        const float* p1 = p0 + 320 + (k + 8) / 4;
+        p0 += k / 4;
+#pragma unroll 4
+        for (int sl = q; sl < slots; sl += FN_SPLIT)
+          s += (double)__ldg(p0 + (size_t)sl * slot_stride) + (double)__ldg(p1 + (size_t)sl * slot_stride);
+      }
       part[q * K + k] = s;
     }
   }
@@ -745,7 +759,7 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
   return cudaGetLastError();
 }
 
-cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad,
+cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad, int layout,
                             float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st) {
   const size_t smem = (size_t)((2 + FN_SPLIT) * bank.K + 32) * sizeof(double);
   if (smem > 48 * 1024) {
@@ -753,7 +767,7 @@ cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slot
         cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  finalize_kernel<<<bank.C, FN_THREADS, smem, st>>>(bank, ws_partials, slots, Cpad, Kpad, grad_low, grad_band,
+  finalize_kernel<<<bank.C, FN_THREADS, smem, st>>>(bank, ws_partials, slots, Cpad, Kpad, layout, grad_low, grad_band,
                                                     grad_filters);
   count_launch();
   return cudaGetLastError();

@@ -75,7 +75,7 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
                                   int gy_dtype, float* ws_partials, int* slots_used, int64_t B,
                                   int64_t T, const DeviceInfo& di, cudaStream_t st);
 // reduces the partial tiles (fp64, fixed order) and applies the synthesis chain rule in fp64
-cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad,
+cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad, int layout,
                             float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st);
 
 // ---- tcgen05 engine (sinc_tc_fwd.cu, ...) -------------------------------------------------------------
@@ -83,5 +83,10 @@ bool tc_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const
 cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
                           const DeviceInfo& di, cudaStream_t st);
 int read_tc_status(int* out);
+int* tc_status_device_ptr();  // device address of the shared 'barrier wait timed out' flag
+bool tc_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
+size_t tc_bwd_filter_partial_bytes(int C);
+cudaError_t launch_bwd_filter_tc(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, float* ws_partials,
+                                 int* slots_used, int64_t B, int64_t T, const DeviceInfo& di, cudaStream_t st);
 
 }  // namespace sinc

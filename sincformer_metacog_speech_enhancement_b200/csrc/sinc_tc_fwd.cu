@@ -282,6 +282,12 @@ cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, 
   return cudaGetLastError();
 }
 
+int* tc_status_device_ptr() {
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, g_tc_status) != cudaSuccess) return nullptr;
+  return reinterpret_cast<int*>(p);
+}
+
 int read_tc_status(int* out) {
   int v = 0;
   cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_status, sizeof(int));

@@ -101,3 +101,56 @@ def test_tc_engine_refuses_unsupported_shapes(tc_engine):
     big = sb.SincConv1d(4, 301, sample_rate=8000).to(dev())
     with pytest.raises(RuntimeError, match="engine"):
         big(torch.randn(1, 1, 1024, device=dev()))          # K + 3 > 256
+
+
+TC_BWD_SHAPES = [
+    (64, 251, 16000, 2, 1000),
+    (64, 251, 16000, 3, 4100),
+    (64, 251, 8000, 5, 100),
+    (64, 251, 8000, 2, 4),
+    (64, 251, 16000, 40, 2048),     # several tiles per CTA slot and more than one flush for some CTAs
+    (8, 250, 8000, 2, 2048),
+    (70, 31, 44100, 2, 776),
+    (130, 9, 8000, 1, 600),
+    (3, 311, 16000, 2, 1536),       # forward falls back to FMA (K > 253); grad-filter TC holds K <= 312
+    (4, 1, 8000, 2, 64),
+]
+
+
+@pytest.mark.parametrize("C,K,sr,B,T", TC_BWD_SHAPES)
+def test_tc_backward_vs_oracle(C, K, sr, B, T):
+    orc, dut = make_pair(C, K, sr)
+    gen = torch.Generator().manual_seed(C * 13 + T)
+    with torch.no_grad():
+        orc.low_hz_.mul_(1 + 0.1 * (2 * torch.rand(orc.low_hz_.shape, generator=gen) - 1))
+        orc.band_hz_.mul_(1 + 0.1 * (2 * torch.rand(orc.band_hz_.shape, generator=gen) - 1))
+    dut.load_state_dict(orc.state_dict())
+    x = torch.randn(B, 1, T, generator=gen)
+    g = torch.randn(B, C, T, generator=gen)
+    sb.set_engine("tc" if K <= 253 else "auto")
+    lib = _lib.load()
+    try:
+        if K > 253:
+            # engine 'tc' would refuse the forward; drive the backward entry point's TC path through AUTO + env
+            pytest.skip("K > 253: forward TC unsupported, covered by the FMA engine")
+        out = run_dut(dut, x, g)
+        mask = lib.sinc_last_engine_mask()
+    finally:
+        sb.set_engine("auto")
+    assert mask & 4, "grad-filter did not run on the tcgen05 engine"
+    assert tc_status() == 0
+    check_against(orc, out, x, g)
+
+
+def test_tc_backward_long_accumulation(tc_engine):
+    """Many tiles per CTA: several accumulator flushes, fp32 accumulation chains of 4096 samples."""
+    torch.manual_seed(1)
+    orc, dut = make_pair(64, 251, 16000)
+    B, T = 16, 48000
+    x = torch.randn(B, 1, T)
+    g = torch.randn(B, 64, T)
+    out = run_dut(dut, x, g, need_x=False)
+    assert tc_status() == 0
+    o64 = O.full_backward(orc, x, g, torch.float64)
+    assert max_rel(out["gfilt"], o64["gfilt"]) <= 1e-5
+    assert max_rel(out["g_low"], o64["g_low"]) <= 1e-4 and max_rel(out["g_band"], o64["g_band"]) <= 1e-4

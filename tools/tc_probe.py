@@ -90,6 +90,49 @@ def run(case):
         imgB, dB, b_step = x.copy(), smem_desc(128, 16), 128
         idc = idesc(M, N, 1, 1)
         expect = Am @ Bm.T
+    elif case.startswith("map_"):
+        # address-mapping probe: fill the MN-major operand's smem image with word indices (split in two 11-bit
+        # digits so every value is exact in TF32), multiply by a K-major one-hot operand, read the mapping off D.
+        # case = map_{a|b}_{lbo}_{sbo}[_n{N}]
+        parts = case.split("_")
+        which, lbo_v, sbo_v = parts[1], int(parts[2]), int(parts[3])
+        N, ks, Kt = 64, 1, 8
+        words = 4096
+        res = {"case": case}
+        maps = []
+        for digit in (0, 1):
+            idx = np.arange(words)
+            img = ((idx >> (11 * digit)) & 2047).astype(np.float32)
+            eye_rows = M if which == "b" else N
+            onehot = np.zeros((eye_rows, Kt), np.float32)
+            # logical K index k selected by row k of the K-major operand
+            for k in range(Kt):
+                onehot[k, k] = 1.0
+            imgK = kmajor_image(onehot, 128, 256)
+            dK = smem_desc(128, 256)
+            dev = torch.device("cuda:0")
+            if which == "a":
+                tA, tB, dA_, dB_, a_mn, b_mn = img, imgK, smem_desc(lbo_v, sbo_v), dK, 1, 0
+            else:
+                tA, tB, dA_, dB_, a_mn, b_mn = imgK, img, dK, smem_desc(lbo_v, sbo_v), 0, 1
+            tA = torch.from_numpy(np.ascontiguousarray(tA)).to(dev)
+            tB = torch.from_numpy(np.ascontiguousarray(tB)).to(dev)
+            D = torch.full((M, N), -777.0, device=dev)
+            st = torch.zeros(1, dtype=torch.int32, device=dev)
+            rc = lib.sinc_tc_probe(ctypes.c_void_p(tA.data_ptr()), tA.numel() * 4, ctypes.c_void_p(tB.data_ptr()),
+                                   tB.numel() * 4, dA_, dB_, idesc(M, N, a_mn, b_mn), 1, 0, 0, 0, 0, N,
+                                   ctypes.c_void_p(D.data_ptr()), ctypes.c_void_p(st.data_ptr()), None)
+            torch.cuda.synchronize()
+            maps.append(D.cpu().numpy())
+            res["rc"], res["status"] = rc, int(st.item())
+        if which == "a":
+            addr = (maps[0][:, :Kt] + 2048 * maps[1][:, :Kt]).astype(np.int64)      # [m][k] -> word index
+        else:
+            addr = (maps[0][:Kt, :].T + 2048 * maps[1][:Kt, :].T).astype(np.int64)  # [n][k] -> word index
+        res["word_addr_rows0_11"] = addr[:12].tolist()
+        res["word_addr_rows_16_32_64"] = [addr[16 if addr.shape[0] > 16 else 0].tolist(), addr[32].tolist(), addr[min(63, addr.shape[0] - 1)].tolist()]
+        print(json.dumps(res))
+        return res
     elif case.startswith("mn_"):
         # isolate MN-major semantics: one operand MN-major, the other canonical K-major
         N, ks = 64, 3
