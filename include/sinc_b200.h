@@ -77,7 +77,7 @@ uint64_t sinc_kernel_launch_count(void);
 /* Select the kernel family for subsequent calls from this process (SINC_ENGINE_*). */
 int sinc_set_engine(int engine);
 int sinc_get_engine(void);
-/* Which engine the last successful sinc_forward / sinc_backward call on this thread actually used:
+/* Which engine the last successful sinc_forward / sinc_backward call of this process actually used:
  * bit 0 forward, bit 1 grad-input, bit 2 grad-filter; a set bit means tcgen05, clear means FMA. */
 int sinc_last_engine_mask(void);
 

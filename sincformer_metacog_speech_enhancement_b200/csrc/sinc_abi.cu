@@ -9,7 +9,8 @@ namespace sinc {
 
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
-static thread_local int t_last_mask = 0;
+// last engine mask: process-wide (backward runs on autograd's own thread, so thread-local would hide it)
+static std::atomic<int> t_last_mask{0};
 // AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
 constexpr bool kAutoPrefersTcForward = true;  // parity-green on B200 (tests/test_gpu_tc.py, r01c)
 constexpr bool kAutoPrefersTcBwdFilter = false;
@@ -97,7 +98,7 @@ int sinc_set_engine(int engine) {
   return 0;
 }
 int sinc_get_engine(void) { return g_engine.load(); }
-int sinc_last_engine_mask(void) { return t_last_mask; }
+int sinc_last_engine_mask(void) { return t_last_mask.load(); }
 
 int sinc_tc_status(int* status_host) {
   if (!status_host) return SINC_E_NULL;
@@ -147,7 +148,7 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
     e = launch_fwd_fma(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return (int)e;
-  t_last_mask = (t_last_mask & ~1) | (use_tc ? 1 : 0);
+  t_last_mask.store((t_last_mask.load() & ~1) | (use_tc ? 1 : 0));
   return 0;
 }
 
@@ -191,7 +192,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     if (e != cudaSuccess) return (int)e;
     mask |= use_tc ? 4 : 0;
   }
-  t_last_mask = (t_last_mask & 1) | mask;
+  t_last_mask.store((t_last_mask.load() & 1) | mask);
   return 0;
 }
 
