@@ -26,7 +26,7 @@
 
 namespace sinc {
 
-constexpr int GF_THREADS = 192;
+constexpr int GF_THREADS = 320;  // warps 0-3, 6-9: grad_y producers; 4: MMA issuer; 5: waveform producer
 constexpr int GF_N = 80;                   // MMA N (tap columns per shift rho)
 constexpr int GF_XSTAGE = 512;             // samples per tile = 32 K-steps of 16 samples
 constexpr int GF_XLEN = GF_XSTAGE + 4 * GF_N + 16;  // floats per shifted waveform array
@@ -98,15 +98,20 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
   const int64_t my_tiles = tile_end - tile_begin;
   bool ok = true;
 
-  if (warp < 4) {
-    // ------------- grad_y producer (global -> TF32 hi/lo -> TMEM ring) and accumulator flusher ---------
-    const int m = tid;                 // TMEM lane = A row (c_local, h)
+  if (warp < 4 || warp >= 6) {
+    // ------------- grad_y producers (global -> TF32 hi/lo -> TMEM ring); group 0 also flushes --------------
+    // Two groups of four warps (one warp per TMEM lane quarter each) take alternate K-steps, which doubles the
+    // bytes in flight per SM: a single group left the DRAM latency exposed (ncu r01g: long-scoreboard stall on
+    // the first use of the loaded data, tensor pipe 39 % active).
+    const int grp = warp < 4 ? 0 : 1;
+    const int quarter = warp & 3;
+    const int m = 32 * quarter + lane;  // TMEM lane = A row (c_local, h)
     const int cl = m >> 1, h = m & 1;
     const int c = c0 + cl;
     const bool row_valid = c < C;
-    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
     float* myslot = a.partials + (((size_t)slot * a.nblk + fblk) * 128 + m) * GF_DCOLS;
-    int64_t kc = 0;  // K-steps produced so far (ring position)
+    int64_t kc0 = 0;  // K-steps before the current tile (ring position of its first K-step)
     bool first_flush = true;
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_begin + it;
@@ -115,27 +120,30 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
       const int64_t left = T - tb;
       const int nq = (int)((left < GF_XSTAGE ? left : GF_XSTAGE) + 15) / 16;
       const float* grow = a.g + (b * C + (row_valid ? c : 0)) * T + tb + 8 * h;
-      // software pipeline: 4 K-steps (2 x LDG.128 each) in flight ahead of the conversion
+      const int qfirst = (int)((kc0 + grp) & 1);  // this group's first K-step in the tile: parity of kc == grp
+      const int nmine = nq > qfirst ? (nq - qfirst + 1) / 2 : 0;
+      // software pipeline: 4 of this group's K-steps (2 x LDG.128 each) in flight ahead of the conversion
       float4 cur[8], nxt[8];
-      auto load4 = [&](float4 (&dst)[8], int q0) {
+      auto load4 = [&](float4 (&dst)[8], int i0) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int q = q0 + u;
+          const int q = qfirst + 2 * (i0 + u);
           const int64_t t = tb + 16 * q + 8 * h;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
-            const bool in = row_valid && q < nq && (t + 4 * j) < T;
+            const bool in = row_valid && (i0 + u) < nmine && (t + 4 * j) < T;
             dst[2 * u + j] = in ? __ldg(reinterpret_cast<const float4*>(grow + 16 * q + 4 * j))
                                 : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
       };
       load4(cur, 0);
-      for (int q0 = 0; q0 < nq; q0 += 4) {
-        if (q0 + 4 < nq) load4(nxt, q0 + 4);
+      for (int i0 = 0; i0 < nmine; i0 += 4) {
+        if (i0 + 4 < nmine) load4(nxt, i0 + 4);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (q0 + u < nq) {
+          if (i0 + u < nmine) {
+            const int64_t kc = kc0 + qfirst + 2 * (i0 + u);
             const int s = (int)(kc % GF_RING);
             const uint32_t par = (uint32_t)((kc / GF_RING) & 1);
             ok = tc::mbar_wait(&a_empty[s], par ^ 1) && ok;
@@ -156,15 +164,15 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&a_full[s]);
-            ++kc;
           }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
       }
-      // flush the TMEM accumulators into this CTA's partial tile
+      kc0 += nq;
+      // flush the TMEM accumulators into this CTA's partial tile (group 0)
       const bool flush_now = ((it + 1) % GF_FLUSH == 0) || (it + 1 == my_tiles);
-      if (flush_now) {
+      if (flush_now && grp == 0) {
         const uint32_t fpar = (uint32_t)((it / GF_FLUSH) & 1);
         ok = tc::mbar_wait(d_full, fpar) && ok;
         tc::fence_after_sync();
@@ -191,7 +199,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
         if (lane == 0) tc::mbar_arrive(d_empty);
       }
     }
-    if (my_tiles == 0) {  // idle CTA: its partial tile must still read as zero
+    if (my_tiles == 0 && grp == 0) {  // idle CTA: its partial tile must still read as zero
       for (int i = 0; i < GF_DCOLS; i += 4) *reinterpret_cast<float4*>(myslot + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   } else if (warp == 4) {
@@ -238,7 +246,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp == 5) {
     // ------------- waveform producer: four shifted TF32 hi/lo copies of the tile -----------------------
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_begin + it;
