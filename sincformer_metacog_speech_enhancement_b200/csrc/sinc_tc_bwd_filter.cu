@@ -26,7 +26,7 @@
 
 namespace sinc {
 
-constexpr int GF_THREADS = 320;  // warps 0-3, 6-9: grad_y producers; 4: MMA issuer; 5: waveform producer
+constexpr int GF_THREADS = 416;  // warps 0-3, 9-12: grad_y producers; 4-7: MMA issuers (one per shift rho); 8: waveform producer
 constexpr int GF_N = 80;                   // MMA N (tap columns per shift rho)
 constexpr int GF_XSTAGE = 512;             // samples per tile = 32 K-steps of 16 samples
 constexpr int GF_XLEN = GF_XSTAGE + 4 * GF_N + 16;  // floats per shifted waveform array
@@ -73,13 +73,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
   if (tid == 0) {
     for (int i = 0; i < GF_RING; ++i) {
       tc::mbar_init(&a_full[i], 4);
-      tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&a_empty[i], 4);   // one tcgen05.commit per issuer warp
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&x_full[i], 1);
-      tc::mbar_init(&x_empty[i], 1);
+      tc::mbar_init(&x_empty[i], 4);
     }
-    tc::mbar_init(d_full, 1);
+    tc::mbar_init(d_full, 4);
     tc::mbar_init(d_empty, 4);
     tc::mbar_init_fence();
   }
@@ -98,13 +98,13 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
   const int64_t my_tiles = tile_end - tile_begin;
   bool ok = true;
 
-  if (warp < 4 || warp >= 6) {
+  if (warp < 4 || warp >= 9) {
     // ------------- grad_y producers (global -> TF32 hi/lo -> TMEM ring); group 0 also flushes --------------
     // Two groups of four warps (one warp per TMEM lane quarter each) take alternate K-steps, which doubles the
     // bytes in flight per SM: a single group left the DRAM latency exposed (ncu r01g: long-scoreboard stall on
     // the first use of the loaded data, tensor pipe 39 % active).
     const int grp = warp < 4 ? 0 : 1;
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;  // tcgen05.ld/st: a warp reaches TMEM lanes 32*(warp%4) .. +31 only
     const int m = 32 * quarter + lane;  // TMEM lane = A row (c_local, h)
     const int cl = m >> 1, h = m & 1;
     const int c = c0 + cl;
@@ -202,13 +202,18 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
     if (my_tiles == 0 && grp == 0) {  // idle CTA: its partial tile must still read as zero
       for (int i = 0; i < GF_DCOLS; i += 4) *reinterpret_cast<float4*>(myslot + i) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-  } else if (warp == 4) {
-    // ------------- MMA issuer ---------------------------------------------------------------------------
+  } else if (warp < 8) {
+    // ------------- MMA issuers: warp 4+rho owns accumulator D_rho ---------------------------------------
+    // One thread can issue a small tcgen05.mma only every ~100 cycles (ncu r01g: the single issuer warp was
+    // busy the whole time while the tensor pipe idled 61 %); the four shifts rho have independent accumulators,
+    // so four warps issue them concurrently and each keeps its own in-order stream.
     if (lane == 0) {
+      const int rho = warp - 4;
       const uint32_t idesc = tc::make_idesc_tf32(128, GF_N, 0, 0);
       const uint64_t bdesc = tc::make_smem_desc(16, 128);  // in-place Toeplitz view, row pitch 4 samples
+      const uint32_t d = tmem + GF_N * rho;
       int64_t kc = 0;
-      uint32_t acc = 0;  // 0: the next K-step overwrites the accumulators
+      uint32_t acc = 0;  // 0: the next K-step overwrites the accumulator
       for (int64_t it = 0; it < my_tiles; ++it) {
         const int64_t tile = tile_begin + it;
         const int64_t b = tile / a.tiles_per_row;
@@ -223,22 +228,20 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
           acc = 0;
         }
         const uint32_t xbase = tc::smem_addr(xs + (size_t)xb * 8 * GF_XLEN);
+        uint64_t bh = tc::desc_at(bdesc, xbase + (2 * rho) * GF_XLEN * 4);
+        uint64_t bl = tc::desc_at(bdesc, xbase + (2 * rho + 1) * GF_XLEN * 4);
         for (int q = 0; q < nq; ++q) {
           const int s = (int)(kc % GF_RING);
           ok = tc::mbar_wait(&a_full[s], (uint32_t)((kc / GF_RING) & 1)) && ok;
           tc::fence_after_sync();
           const uint32_t ah = tmem + GF_DCOLS + 16 * s, al = ah + 8;
-#pragma unroll
-          for (int rho = 0; rho < 4; ++rho) {
-            const uint32_t d = tmem + GF_N * rho;
-            const uint64_t bh = tc::desc_at(bdesc, xbase + (2 * rho) * GF_XLEN * 4 + 64 * q);
-            const uint64_t bl = tc::desc_at(bdesc, xbase + (2 * rho + 1) * GF_XLEN * 4 + 64 * q);
-            tc::mma_tf32_ts(d, ah, bh, idesc, acc);
-            tc::mma_tf32_ts(d, ah, bl, idesc, 1);
-            tc::mma_tf32_ts(d, al, bh, idesc, 1);
-          }
+          tc::mma_tf32_ts(d, ah, bh, idesc, acc);
+          tc::mma_tf32_ts(d, ah, bl, idesc, 1);
+          tc::mma_tf32_ts(d, al, bh, idesc, 1);
           acc = 1;
           tc::mma_commit(&a_empty[s]);
+          bh += 4;  // +64 bytes (16 samples) in the start-address field
+          bl += 4;
           ++kc;
         }
         tc::mma_commit(&x_empty[xb]);
@@ -246,7 +249,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
+  } else if (warp == 8) {
     // ------------- waveform producer: four shifted TF32 hi/lo copies of the tile -----------------------
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_begin + it;

@@ -31,7 +31,7 @@ namespace sinc {
 // set to 1 by any tcgen05 kernel whose barrier wait timed out (a protocol bug): read by sinc_tc_status()
 __device__ int g_tc_status = 0;
 
-constexpr int TF_THREADS = 192;
+constexpr int TF_THREADS = 224;  // warps 0-3 epilogue, 4 and 6 MMA issuers (even / odd tiles), 5 waveform producer
 constexpr int TF_FB = 32;                 // filters per CTA
 constexpr int TF_NJ = 128;                // MMA N: output groups of 4 samples per tile
 constexpr int TF_TT = 4 * TF_NJ;          // 512 output samples per tile
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) fwd_tc_kernel(const FwdTcArgs a
   float* w_lo = stage + TF_FB * TF_WPITCH;      // [32][TF_WPITCH]
   for (int i = tid; i < 2 * TF_FB * TF_WPITCH; i += TF_THREADS) stage[i] = 0.f;
   __syncthreads();
-  for (int cl = warp; cl < TF_FB; cl += TF_THREADS / 32) {
+  for (int cl = warp; cl < TF_FB; cl += TF_THREADS / 32) {  // 7 warps share the 32 filters
     const int c = c0 + cl;
     if (c < C)
       synth_filter_warp(a.bank, c, lane, [&](int k, double w) {
@@ -177,34 +177,40 @@ __global__ void __launch_bounds__(TF_THREADS, 1) fwd_tc_kernel(const FwdTcArgs a
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_full[buf]);
     }
-  } else if (warp == 4) {
-    // ---------------- MMA issuer ---------------------------------------------------------------------
+  } else if (warp == 4 || warp == 6) {
+    // ---------------- MMA issuers: warp 4 takes the even tiles (accumulator 0), warp 6 the odd ones ----------
+    // A single thread issues one small tcgen05.mma per ~100 cycles, more than the 64 cycles an N=128 TF32 MMA
+    // occupies the tensor pipe; two issuers with independent accumulators keep the pipe fed.
     if (lane == 0) {
+      const int buf = warp == 4 ? 0 : 1;
       const uint64_t bdesc = tc::make_smem_desc(16, 128);      // in-place Toeplitz view of the waveform tile
-      const uint64_t adesc = tc::make_smem_desc(128, 8192);    // W'_lo
-      const uint32_t a_lo_addr = tc::smem_addr(a_lo);
-      for (int64_t it = 0; it < my_tiles; ++it) {
-        const int buf = (int)(it & 1);
+      const uint64_t adesc0 = tc::desc_at(tc::make_smem_desc(128, 8192), tc::smem_addr(a_lo));  // W'_lo
+      const uint32_t d = tmem + (uint32_t)(buf * TF_NJ);
+      const uint32_t xh_addr = tc::smem_addr(xbuf + (2 * buf) * TF_XT);
+      const uint64_t bh0 = tc::desc_at(bdesc, xh_addr);
+      const uint64_t bl0 = tc::desc_at(bdesc, xh_addr + TF_XT * 4);
+      for (int64_t it = buf; it < my_tiles; it += 2) {
         const uint32_t par = (uint32_t)((it >> 1) & 1);
         ok = tc::mbar_wait(&acc_empty[buf], par ^ 1) && ok;
         ok = tc::mbar_wait(&x_full[buf], par) && ok;
         tc::fence_after_sync();
-        const uint32_t d = tmem + (uint32_t)(buf * TF_NJ);
-        const uint32_t xh_addr = tc::smem_addr(xbuf + (2 * buf) * TF_XT);
-        const uint32_t xl_addr = xh_addr + TF_XT * 4;
+        uint64_t bh = bh0, bl = bl0, al = adesc0;
+        uint32_t ah = tmem + 256;
         for (int q = 0; q < a.ksteps; ++q) {
-          const uint64_t bh = tc::desc_at(bdesc, xh_addr + 32 * q);
-          const uint64_t bl = tc::desc_at(bdesc, xl_addr + 32 * q);
-          tc::mma_tf32_ts(d, tmem + 256 + 8 * q, bh, idesc, q > 0);
-          tc::mma_tf32_ts(d, tmem + 256 + 8 * q, bl, idesc, 1);
-          tc::mma_tf32_ss(d, tc::desc_at(adesc, a_lo_addr + 256 * q), bh, idesc, 1);
+          tc::mma_tf32_ts(d, ah, bh, idesc, q > 0);
+          tc::mma_tf32_ts(d, ah, bl, idesc, 1);
+          tc::mma_tf32_ss(d, al, bh, idesc, 1);
+          bh += 2;   // +32 bytes (8 taps) in the start-address field
+          bl += 2;
+          al += 16;  // +256 bytes: next two K-chunks of W'_lo
+          ah += 8;
         }
         tc::mma_commit(&x_empty[buf]);
         tc::mma_commit(&acc_full[buf]);
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 4) {
     // ---------------- epilogue: TMEM -> registers -> staging -> bulk stores -------------------------
     const int m = tid, cl = m >> 2, r = m & 3;
     const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
