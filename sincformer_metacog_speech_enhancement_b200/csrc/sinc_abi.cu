@@ -14,6 +14,7 @@ static std::atomic<int> t_last_mask{0};
 // AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
 constexpr bool kAutoPrefersTcForward = true;  // parity-green on B200 (tests/test_gpu_tc.py, r01c)
 constexpr bool kAutoPrefersTcBwdFilter = false;
+constexpr bool kAutoPrefersTcBwdInput = false;
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -171,16 +172,22 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   int mask = 0;
+  const int engine = g_engine.load();
   if (grad_x) {
-    e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
+    const bool tc_ok = tc_bwd_input_supported(bank.C, bank.K, grad_y, gy_dtype, di);
+    const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdInput));
+    if (use_tc)
+      e = launch_bwd_input_tc(bank, grad_y, grad_x, B, T, di, st);
+    else
+      e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
     if (e != cudaSuccess) return (int)e;
+    mask |= use_tc ? 2 : 0;
   }
   if (want_params) {
     const WorkspaceLayout wl = workspace_layout(bank.C, bank.K);
     if (!workspace || workspace_bytes < wl.total_bytes) return SINC_E_WORKSPACE;
     float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
     int slots = 0;
-    const int engine = g_engine.load();
     const bool tc_ok = tc_bwd_filter_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
     const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter));
     if (use_tc)

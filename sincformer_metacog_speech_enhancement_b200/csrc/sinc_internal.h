@@ -89,4 +89,8 @@ size_t tc_bwd_filter_partial_bytes(int C);
 cudaError_t launch_bwd_filter_tc(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, float* ws_partials,
                                  int* slots_used, int64_t B, int64_t T, const DeviceInfo& di, cudaStream_t st);
 
+bool tc_bwd_input_supported(int C, int K, const void* g, int g_dtype, const DeviceInfo& di);
+cudaError_t launch_bwd_input_tc(const Bank& bank, const void* gy, float* gx, int64_t B, int64_t T, const DeviceInfo& di,
+                                cudaStream_t st);
+
 }  // namespace sinc

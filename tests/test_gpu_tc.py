@@ -105,6 +105,9 @@ def test_tc_engine_refuses_unsupported_shapes(tc_engine):
 
 TC_BWD_SHAPES = [
     (64, 251, 16000, 2, 1000),
+    (64, 251, 16000, 1, 16000),
+    (64, 251, 16000, 7, 4099),      # ragged T: grad-input TC takes any T (forward / grad-filter fall back to FMA)
+    (33, 127, 8000, 3, 3000),
     (64, 251, 16000, 3, 4100),
     (64, 251, 8000, 5, 100),
     (64, 251, 8000, 2, 4),
@@ -127,17 +130,28 @@ def test_tc_backward_vs_oracle(C, K, sr, B, T):
     dut.load_state_dict(orc.state_dict())
     x = torch.randn(B, 1, T, generator=gen)
     g = torch.randn(B, C, T, generator=gen)
-    sb.set_engine("tc" if K <= 253 else "auto")
     lib = _lib.load()
+    # the forward runs under AUTO (engine "tc" refuses shapes its forward cannot take); the backward under "tc"
+    xd = x.to(dev()).clone().requires_grad_(True)
+    for p in dut.parameters():
+        p.grad = None
+    from sincformer_metacog_speech_enhancement_b200.sinc import SincConvFunction
+    SincConvFunction._expose_grad_filters = True
     try:
-        if K > 253:
-            # engine 'tc' would refuse the forward; drive the backward entry point's TC path through AUTO + env
-            pytest.skip("K > 253: forward TC unsupported, covered by the FMA engine")
-        out = run_dut(dut, x, g)
+        y = dut(xd)
+        sb.set_engine("tc")
+        y.backward(g.to(dev()))
+        torch.cuda.synchronize()
         mask = lib.sinc_last_engine_mask()
     finally:
         sb.set_engine("auto")
-    assert mask & 4, "grad-filter did not run on the tcgen05 engine"
+        SincConvFunction._expose_grad_filters = False
+    out = dict(y=y.detach().cpu(), gx=xd.grad.cpu(), gfilt=SincConvFunction._last_grad_filters.cpu(),
+               g_low=dut.low_hz_.grad.cpu(), g_band=dut.band_hz_.grad.cpu())
+    if T % 4 == 0 and K <= 312:
+        assert mask & 4, "grad-filter did not run on the tcgen05 engine"
+    if C <= 64 and K <= 256:
+        assert mask & 2, "grad-input did not run on the tcgen05 engine"
     assert tc_status() == 0
     check_against(orc, out, x, g)
 
