@@ -13,8 +13,8 @@ static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
 static std::atomic<int> t_last_mask{0};
 // AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
 constexpr bool kAutoPrefersTcForward = true;  // parity-green on B200 (tests/test_gpu_tc.py, r01c)
-constexpr bool kAutoPrefersTcBwdFilter = false;
-constexpr bool kAutoPrefersTcBwdInput = false;
+constexpr bool kAutoPrefersTcBwdFilter = true;  // parity-green on B200 (r01h)
+constexpr bool kAutoPrefersTcBwdInput = true;   // parity-green on B200 (r01j)
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
