@@ -12,10 +12,11 @@
 // issuer warp and four epilogue warps per half.
 //
 // col2im without atomics or bank conflicts (per epilogue warp, lanes = 32 consecutive positions):
-//   phase 1  lane l stores P[t'_l, k] to R[(k + l) % 64][l]            (one wavefront per column k)
-//   phase 2  lane j owns output row tau = 32*blk + j and reads R[tau][(s + j) % 32], s = 0..31 (rotated: conflict
-//            free), keeping the cells whose tap k = tau - lane lies in this half
-// then adds its 32 sums to the warp's private window; the eight windows and the carry from earlier stages are
+//   phase 1  for a chunk of 32 taps, lane l stores P[t'_l, k0 + j] to S[l][l + j]  (skewed band in a 32 x 64 buffer
+//            that is zero outside the band; row pitch 64 makes every store instruction one wavefront)
+//   phase 2  lane j sums columns j and 32 + j over the 32 rows (immediate-offset LDS, one wavefront each);
+//            the upper 32 column sums overlap the next chunk and are carried in a register
+// and writes the sums to the warp's private window; the eight windows and the carry from earlier stages are
 // combined in a fixed order, the 128 oldest outputs are complete and written, the rest is carried.  Bitwise
 // reproducible.  A CTA owns a contiguous range of 128-sample output blocks and recomputes the 2H-column halo
 // at the start of each run instead of exchanging partial sums with its neighbour.
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
       // ------------- epilogue: TMEM -> col2im -> window -> gx -------------------------------------------------
       const int hf = warp >> 2, quarter = warp & 3;
       const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
-      float* R = rring + warp * 64 * 32;
+      float* S = rring + warp * 64 * 32;          // [32 rows][64] skew buffer, zero outside the band
       float* win = outw + warp * GI_WIN;
       const int obase = 32 * quarter + 128 * hf;  // window index of (lane 0, tap 128*hf)
       tc::named_bar_sync(2, 256);                 // previous run's carry writes are done
@@ -199,35 +200,35 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
         const int64_t c0 = s_out - H + (int64_t)GI_NS * i;  // first position of the stage
         ok = tc::mbar_wait(&d_full[hf], (uint32_t)(sg & 1)) && ok;
         tc::fence_after_sync();
+        float tail = 0.f;  // column sums of the upper 32 rows of the previous chunk (they overlap the next chunk)
 #pragma unroll 1
-        for (int ch = 0; ch < 5; ++ch) {
-          if (ch < 4) {
-            uint32_t vv[32];
-            tc::tmem_ld32(tmem + lane_base + 128 * hf + 32 * ch, vv);
-            tc::tmem_ld_wait();
-            if (ch == 3) {  // all 128 columns of this half are in registers / smem: release the accumulator
-              tc::fence_before_sync();
-              __syncwarp();
-              if (lane == 0) tc::mbar_arrive(&d_empty[hf]);
-            }
-#pragma unroll
-            for (int j = 0; j < 32; ++j) R[((32 * ch + j + lane) & 63) * 32 + lane] = __uint_as_float(vv[j]);
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t vv[32];
+          tc::tmem_ld32(tmem + lane_base + 128 * hf + 32 * ch, vv);
+          tc::tmem_ld_wait();
+          if (ch == 3) {  // all 128 columns of this half have left TMEM: release the accumulator
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&d_empty[hf]);
           }
+          // phase 1: lane l writes its 32 values to S[l][l + j] (skewed band; cells outside the band stay zero)
+          float* srow = S + lane * 65;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) srow[j] = __uint_as_float(vv[j]);
           __syncwarp();
-          // rows tau in [32 ch, 32 ch + 32) are complete: lane owns tau = 32 ch + lane
-          const int tau = 32 * ch + lane;
-          const float* row = R + (tau & 63) * 32;
-          float sum = 0.f;
+          // phase 2: column sums; lane owns columns tau = lane and tau = 32 + lane of the 64-wide band
+          float s0 = 0.f, s1 = 0.f;
+          const float* col = S + lane;
 #pragma unroll
-          for (int s = 0; s < 32; ++s) {
-            const int lr = (s + lane) & 31;
-            const int kl = tau - lr;  // tap within this half
-            const float val = row[lr];
-            sum += (kl >= 0 && kl < 128) ? val : 0.f;
+          for (int l2 = 0; l2 < 32; ++l2) {
+            s0 += col[l2 * 64];
+            s1 += col[l2 * 64 + 32];
           }
-          win[obase + tau] = sum;  // every window cell of this warp is written exactly once per stage
+          win[obase + 32 * ch + lane] = s0 + tail;  // every window cell of this warp is written once per stage
+          tail = s1;
           __syncwarp();
         }
+        win[obase + 128 + lane] = tail;
         // combine the eight windows with the carry in a fixed order; the first 128 outputs are complete
         tc::named_bar_sync(2, 256);
         float tot[2];
