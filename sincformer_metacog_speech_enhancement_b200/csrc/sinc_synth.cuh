@@ -3,11 +3,9 @@
 // parameters and buffers, one warp per filter.  Every convolution kernel calls this in its prologue
 // (no separate synthesis launch, no filter tensor in HBM).
 //
-// Why fp64: sin(f_high*n) - sin(f_low*n) cancels ~25x (the band is a few % of the cut-off), so an
-// fp32 evaluation carries ~1.5e-6 relative error -- that is the reference's own distance from exact
-// arithmetic.  Evaluating in fp64 keeps OUR distance from the fp32 reference at exactly that figure
-// instead of the sum of two independent fp32 errors.  The cost is
-// 2*H fp64 sin per filter, once per persistent CTA (a few microseconds).
+// Accuracy target: stay within ~3e-7 of the reference evaluated in fp64, so that OUR distance from the fp32
+// reference is the reference's own round-off (2e-6 .. 2e-5) and not the sum of two independent fp32 errors
+// (SURVEY.md section 7 step 3, H4).  See synth_filter_warp for how that is done without fp64 transcendentals.
 #pragma once
 #include "sinc_internal.h"
 
@@ -45,53 +43,64 @@ __device__ __forceinline__ double left_tap(const ChanCoef& cc, double nj) {
   return (sin(cc.f_hi * nj) - sin(cc.f_lo * nj)) / (nj * 0.5 + 1e-8);
 }
 
-// Whole-warp call.  Synthesises filter `c` and calls emit(k, w_k) for every tap k in [0,K) exactly
-// once (from varying lanes).  Optionally returns the un-normalised taps through emit_u(k, u_k) and
-// the normaliser S = sum|u| + 1e-8 (used by the backward's chain rule).
+// Whole-warp call.  Synthesises filter `c` and calls emit(k, w_k) (w_k as double) for every tap k in [0,K)
+// exactly once (from varying lanes).
+//
+// Arithmetic: the per-filter scalars are fp64; each tap is evaluated in fp32 through the cancellation-free
+// identity  sin(a) - sin(b) = 2 cos((a+b)/2) sin((a-b)/2)  and the L1 norm is accumulated in fp64.  The
+// reference's own form sin(f_hi n) - sin(f_lo n) cancels 10-25x in fp32 (that is why it sits 2e-6 .. 2e-5 from
+// its fp64 evaluation); the product form has no cancellation, so fp32 gives ~3e-7 of the fp64 value at a
+// sixteenth of the latency of fp64 sin (ncu r01m: the fp64 prologue was 10 % of the tensor-core kernels).
 template <class Emit>
 __device__ __noinline__ void synth_filter_warp(const Bank& bk, int c, int lane, Emit emit,
                                                double* S_out = nullptr) {
   const int K = bk.K;
   const int H = (K - 1) / 2;
   const ChanCoef cc = chan_coef(bk, c);
+  const float fs = (float)(0.5 * (cc.f_hi + cc.f_lo));  // (a+b)/2 = fs * n
+  const float fd = (float)(0.5 * (cc.f_hi - cc.f_lo));  // (a-b)/2 = fd * n
+  auto left32 = [&](int j) -> float {
+    const float nj = bk.n[j];
+    return 2.0f * cosf(fs * nj) * sinf(fd * nj) / (nj * 0.5f + 1e-8f);
+  };
   constexpr int R = 4;  // taps cached in registers per lane: covers H <= 128 (K <= 257)
-  double ul[R], ur[R];
+  float ul[R], ur[R];
   double sumabs = 0.0;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = r * 32 + lane;
-    double l = 0.0, rr = 0.0;
+    float l = 0.f, rr = 0.f;
     if (j < H) {
-      const double left = left_tap(cc, (double)bk.n[j]);
-      l = left * (double)bk.window[j];           // :105-111, tap j
-      rr = left * (double)bk.window[K - 1 - j];  // mirrored tap K-1-j (window is NOT symmetric)
-      sumabs += fabs(l) + fabs(rr);
+      const float left = left32(j);
+      l = left * bk.window[j];           // :105-111, tap j
+      rr = left * bk.window[K - 1 - j];  // mirrored tap K-1-j (the window is NOT symmetric)
+      sumabs += (double)fabsf(l) + (double)fabsf(rr);
     }
     ul[r] = l;
     ur[r] = rr;
   }
   for (int j = R * 32 + lane; j < H; j += 32) {  // long filters: second pass recomputes these
-    const double left = left_tap(cc, (double)bk.n[j]);
-    sumabs += fabs(left * (double)bk.window[j]) + fabs(left * (double)bk.window[K - 1 - j]);
+    const float left = left32(j);
+    sumabs += (double)fabsf(left * bk.window[j]) + (double)fabsf(left * bk.window[K - 1 - j]);
   }
-  const double uc = 2.0 * (cc.f_hi - cc.f_lo) * (double)bk.window[H];  // :104
-  if (lane == 0) sumabs += fabs(uc);
+  const float uc = (float)(2.0 * (cc.f_hi - cc.f_lo)) * bk.window[H];  // :104
+  if (lane == 0) sumabs += (double)fabsf(uc);
   const double S = warp_sum(sumabs) + 1e-8;  // :112
   if (S_out) *S_out = S;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = r * 32 + lane;
     if (j < H) {
-      emit(j, ul[r] / S);
-      emit(K - 1 - j, ur[r] / S);
+      emit(j, (double)ul[r] / S);
+      emit(K - 1 - j, (double)ur[r] / S);
     }
   }
   for (int j = R * 32 + lane; j < H; j += 32) {
-    const double left = left_tap(cc, (double)bk.n[j]);
-    emit(j, left * (double)bk.window[j] / S);
-    emit(K - 1 - j, left * (double)bk.window[K - 1 - j] / S);
+    const float left = left32(j);
+    emit(j, (double)(left * bk.window[j]) / S);
+    emit(K - 1 - j, (double)(left * bk.window[K - 1 - j]) / S);
   }
-  if (lane == 0) emit(H, uc / S);
+  if (lane == 0) emit(H, (double)uc / S);
 }
 
 // ---- small PTX helpers used by several kernels -------------------------------------------------

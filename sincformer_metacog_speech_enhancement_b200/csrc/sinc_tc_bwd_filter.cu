@@ -152,10 +152,9 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
                                 cur[2 * u + 1].x, cur[2 * u + 1].y, cur[2 * u + 1].z, cur[2 * u + 1].w};
             uint32_t hi[8], lo[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const float fh = tc::to_tf32(v[e]);
-              hi[e] = __float_as_uint(fh);
-              lo[e] = __float_as_uint(tc::to_tf32(v[e] - fh));
+            for (int e = 0; e < 8; ++e) {  // truncation split: hi = top 19 bits, lo = exact remainder (the MMA
+              hi[e] = __float_as_uint(v[e]) & 0xffffe000u;  // ignores the low 13 mantissa bits of lo)
+              lo[e] = __float_as_uint(v[e] - __uint_as_float(hi[e]));
             }
             const uint32_t dst = tmem + lane_base + GF_DCOLS + 16 * s;
             tc::tmem_st8(dst, hi);

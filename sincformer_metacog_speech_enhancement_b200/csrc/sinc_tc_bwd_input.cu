@@ -142,10 +142,9 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
         for (int cb = 0; cb < 64; cb += 8) {
           uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float fh = tc::to_tf32(vv[cb + e]);
-            hi[e] = __float_as_uint(fh);
-            lo[e] = __float_as_uint(tc::to_tf32(vv[cb + e] - fh));
+          for (int e = 0; e < 8; ++e) {  // truncation split: hi = top 19 bits, lo = exact remainder (the MMA
+            hi[e] = __float_as_uint(vv[cb + e]) & 0xffffe000u;  // ignores the low 13 mantissa bits of lo)
+            lo[e] = __float_as_uint(vv[cb + e] - __uint_as_float(hi[e]));
           }
           tc::tmem_st8(dst + cb, hi);
           tc::tmem_st8(dst + 64 + cb, lo);
@@ -220,9 +219,22 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
           float s0 = 0.f, s1 = 0.f;
           const float* col = S + lane;
 #pragma unroll
-          for (int l2 = 0; l2 < 32; ++l2) {
-            s0 += col[l2 * 64];
-            s1 += col[l2 * 64 + 32];
+          for (int h2 = 0; h2 < 2; ++h2) {  // 32 independent loads in flight, then two pairwise trees
+            float t0[16], t1[16];
+#pragma unroll
+            for (int l2 = 0; l2 < 16; ++l2) {
+              t0[l2] = col[(16 * h2 + l2) * 64];
+              t1[l2] = col[(16 * h2 + l2) * 64 + 32];
+            }
+#pragma unroll
+            for (int w2 = 8; w2 > 0; w2 >>= 1)
+#pragma unroll
+              for (int l2 = 0; l2 < w2; ++l2) {
+                t0[l2] += t0[l2 + w2];
+                t1[l2] += t1[l2 + w2];
+              }
+            s0 += t0[0];
+            s1 += t1[0];
           }
           win[obase + 32 * ch + lane] = s0 + tail;  // every window cell of this warp is written once per stage
           tail = s1;

@@ -120,7 +120,7 @@ def test_filter_synthesis_matches_reference(init_kat):
         c, k, sr = key.split("_")
         m = sb.SincConv1d(int(c[1:]), int(k[1:]), sample_rate=int(sr[2:])).to(dev())
         w = m.filters().cpu()
-        assert max_rel(w, init_kat[f"{key}/filters64"]) <= 2e-7      # fp64 synthesis rounded once to fp32
+        assert max_rel(w, init_kat[f"{key}/filters64"]) <= 1e-6      # cancellation-free fp32 taps, fp64 norm
         assert max_rel(w, init_kat[f"{key}/filters32"]) <= 1e-5
 
 
