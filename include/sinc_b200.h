@@ -42,6 +42,7 @@ extern "C" {
 #define SINC_ENGINE_AUTO 0
 #define SINC_ENGINE_FMA 1
 #define SINC_ENGINE_TC 2
+#define SINC_ENGINE_TC_TF32 3 /* tcgen05 kernels, 3xTF32 split in every pass (fp32-grade gradients, half the rate) */
 
 #define SINC_OK 0
 #define SINC_E_NULL (-1)        /* a required pointer is NULL                               */
@@ -78,7 +79,8 @@ uint64_t sinc_kernel_launch_count(void);
 int sinc_set_engine(int engine);
 int sinc_get_engine(void);
 /* Which engine the last successful sinc_forward / sinc_backward call of this process actually used:
- * bit 0 forward, bit 1 grad-input, bit 2 grad-filter; a set bit means tcgen05, clear means FMA. */
+ * bit 0 forward, bit 1 grad-input, bit 2 grad-filter; a set bit means tcgen05, clear means FMA.
+ * Bits 3/4/5 (forward / grad-input / grad-filter): the tcgen05 kernel used 16-bit split operands. */
 int sinc_last_engine_mask(void);
 
 /* Bytes of device scratch sinc_forward / sinc_backward need for this shape (never 0). */

@@ -6,8 +6,9 @@ from . import _lib
 
 
 def set_engine(name: str) -> None:
-    """'auto' (default), 'fma' (FP32 CUDA-core kernels) or 'tc' (tcgen05 tensor-core kernels)."""
-    code = {"auto": _lib.ENGINE_AUTO, "fma": _lib.ENGINE_FMA, "tc": _lib.ENGINE_TC}[name]
+    """'auto' (default), 'fma' (FP32 CUDA-core kernels), 'tc' (tcgen05 tensor-core kernels; 16-bit split operands
+    where the stated tolerance allows) or 'tc_tf32' (tcgen05 with the 3xTF32 split in every pass)."""
+    code = {"auto": _lib.ENGINE_AUTO, "fma": _lib.ENGINE_FMA, "tc": _lib.ENGINE_TC, "tc_tf32": _lib.ENGINE_TC_TF32}[name]
     _lib.check(_lib.load().sinc_set_engine(code), "sinc_set_engine")
 
 

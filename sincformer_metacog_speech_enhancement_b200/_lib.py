@@ -14,7 +14,7 @@ from . import build as _build
 
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
-ENGINE_AUTO, ENGINE_FMA, ENGINE_TC = 0, 1, 2
+ENGINE_AUTO, ENGINE_FMA, ENGINE_TC, ENGINE_TC_TF32 = 0, 1, 2, 3
 
 ABI_SYMBOLS = (
     "sinc_abi_version", "sinc_strerror", "sinc_kernel_launch_count", "sinc_set_engine",

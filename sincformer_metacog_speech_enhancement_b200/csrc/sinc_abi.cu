@@ -94,7 +94,7 @@ const char* sinc_strerror(int code) {
 uint64_t sinc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int sinc_set_engine(int engine) {
-  if (engine < SINC_ENGINE_AUTO || engine > SINC_ENGINE_TC) return SINC_E_ENGINE;
+  if (engine < SINC_ENGINE_AUTO || engine > SINC_ENGINE_TC_TF32) return SINC_E_ENGINE;
   g_engine.store(engine);
   return 0;
 }
@@ -140,7 +140,9 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   const int engine = g_engine.load();
   const bool tc_ok = tc_fwd_supported(bank.C, bank.K, T, y, y_dtype, di);
   if (engine == SINC_ENGINE_TC && !tc_ok) return SINC_E_ENGINE;
-  const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcForward));
+  if (engine == SINC_ENGINE_TC_TF32 && !tc_ok) return SINC_E_ENGINE;
+  const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
+                                (engine == SINC_ENGINE_AUTO && kAutoPrefersTcForward));
   cudaError_t e;
   if (use_tc) {
     e = launch_fwd_tc(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
@@ -175,13 +177,20 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   const int engine = g_engine.load();
   if (grad_x) {
     const bool tc_ok = tc_bwd_input_supported(bank.C, bank.K, grad_y, gy_dtype, di);
-    const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdInput));
-    if (use_tc)
+    const bool tc16_ok = tc16_bwd_input_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
+    const bool want_tc = engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
+                         (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdInput);
+    const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
+    const bool use_tc = want_tc && tc_ok && !use_tc16;
+    if (use_tc16)
+      e = launch_bwd_input_tc16(bank, grad_y, grad_x, B, T, di, st);
+    else if (use_tc)
       e = launch_bwd_input_tc(bank, grad_y, grad_x, B, T, di, st);
     else
       e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
     if (e != cudaSuccess) return (int)e;
-    mask |= use_tc ? 2 : 0;
+    mask |= (use_tc || use_tc16) ? 2 : 0;
+    mask |= use_tc16 ? 16 : 0;
   }
   if (want_params) {
     const WorkspaceLayout wl = workspace_layout(bank.C, bank.K);
@@ -189,7 +198,8 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
     int slots = 0;
     const bool tc_ok = tc_bwd_filter_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
-    const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter));
+    const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
+                                  (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter));
     if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else

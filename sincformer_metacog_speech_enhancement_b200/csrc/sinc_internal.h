@@ -93,4 +93,10 @@ bool tc_bwd_input_supported(int C, int K, const void* g, int g_dtype, const Devi
 cudaError_t launch_bwd_input_tc(const Bank& bank, const void* gy, float* gx, int64_t B, int64_t T, const DeviceInfo& di,
                                 cudaStream_t st);
 
+
+// 16-bit split variants (bf16 hi/mid, three kind::f16 MMAs): sinc_tc16_*.cu
+bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
+cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, float* gx, int64_t B, int64_t T,
+                                  const DeviceInfo& di, cudaStream_t st);
+
 }  // namespace sinc

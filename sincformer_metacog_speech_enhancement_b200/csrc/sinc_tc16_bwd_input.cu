@@ -1,0 +1,377 @@
+// tcgen05 engine, grad-input, 16-bit split operands:
+//     gx[b,t] = sum_c sum_k w[c,k] g[b,c,t-k+H]                        (ConvolutionBackward0, grad-input)
+// as a GEMM over (tap parity, filter) + a skewed column sum (col2im), bf16 hi/mid split, sm_100a only.
+//
+// Precision.  Every fp32 operand is split v = hi + mid, hi = bf16(v), mid = bf16(v - hi) (16 significant bits);
+// three kind::f16 MMAs (hi*hi + hi*mid + mid*hi) accumulate in fp32.  Measured against the fp64 oracle the result
+// is ~6e-6 max-norm relative -- 16x inside the 1e-4 gradient gate -- at twice the tensor-core rate of the 3xTF32
+// kernel (sinc_tc_bwd_input.cu, kept as the SINC_ENGINE_TC_TF32 variant).
+//
+// Formulation.  Taps are paired, k = 2k' + e.  With  D[k', p] = sum_e sum_c w[c, 2k'+e] * g[c, p-e]  every
+// element of D belongs to ONE output, t = p + 2k' - H, so the GEMM does half of the col2im additions itself:
+//     A = W'[k', (e,c)] = w[c, 2k'+e]      128 tap pairs x K = 2*64, resident in TMEM (hi and mid) for the whole kernel
+//     B = G [p , (e,c)] = g[c, p-e]        positions x K, K-major in shared memory
+// B is stored ONCE per position as 8 "planes" of 16-byte rows (8 filters each): a K-major no-swizzle operand
+// with SBO = 128 is a plain row-pitch-16-byte matrix, so the e = 1 half of K is the same memory read one row
+// earlier (start address - 16 bytes): no duplication, no im2col.  Shared memory holds no filters at all.
+//
+// col2im (per epilogue warp: 32 tap pairs x 32 positions from tcgen05.ld, cell (L, j) belongs to output 2L + j):
+//   store   lane L = 16h + a writes its 32 values to S[h*545 + 34a + j]           (32 conflict-free STS)
+//   gather  lane r reads S[h*545 + 32m + r], m = 0..16: the cell is (a = m, j = r - 2m), output r, when 2m <= r,
+//           and (a = m-1, j = r - 2m + 34), output r + 32, when 2m >= r + 3 -- two mask FMAs per load
+// i.e. 66 shared-memory wavefronts per 1024 accumulator values (the 3xTF32 kernel spends 96 on half as many
+// MMA flops per value).  Sums are carried across the two 32-column chunks in registers, the eight warps'
+// 128-cell windows and the carry from earlier stages are combined in a fixed order: bitwise reproducible.
+//
+// Pipeline: 4 producer warps (global -> bf16 hi/mid -> planes, 4-slot ring; the last row of a stage is also the
+// halo row of the next), 2 MMA issuer warps (one per 64-column half), double-buffered accumulators in TMEM,
+// 8 epilogue warps.  A CTA owns a contiguous range of 128-sample output blocks and recomputes the 2H-column halo
+// at the start of each run.
+#include <cuda_bf16.h>
+
+#include "sinc_internal.h"
+#include "sinc_synth.cuh"
+#include "sinc_tc.cuh"
+
+namespace sinc {
+
+constexpr int H2_THREADS = 448;  // warps 0-7 epilogue (quarter = w%4, column half = w/4), 8-9 issuers, 10-13 producers
+constexpr int H2_NS = 128;       // D columns (positions) per stage
+constexpr int H2_SLOTS = 4;      // B ring depth
+constexpr int H2_PLANE = (H2_NS + 1) * 16;       // bytes: halo row + 128 rows of 8 filters x bf16
+constexpr int H2_SLOT = 2 * 8 * H2_PLANE;        // hi planes [8], mid planes [8]
+constexpr int H2_WIN = 384;                      // output window of one stage: 128 positions + 2*127 + 1
+constexpr int H2_SKEW = 1092;                    // floats per epilogue warp: 2 regions of 16 rows x pitch 34 (+1)
+constexpr int H2_SM_G = 0;                                     // B ring; in the prologue: fp32 filters [64][256]
+constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // skew buffers
+constexpr int H2_SM_OUT = H2_SM_S + 8 * H2_SKEW * 4;           // 8 x window [128]
+constexpr int H2_SM_CARRY = H2_SM_OUT + 8 * 128 * 4;           // carry [256]
+constexpr int H2_SM_BAR = H2_SM_CARRY + 256 * 4;
+constexpr int H2_SM_TOTAL = H2_SM_BAR + 256;
+static_assert(64 * 256 * 4 <= H2_SLOTS * H2_SLOT, "filter staging must fit in the B ring");
+static_assert(H2_SM_S % 16 == 0 && H2_SM_OUT % 16 == 0, "alignment");
+
+struct BwdInputTc16Args {
+  Bank bank;
+  const float* g;
+  float* gx;
+  int64_t B, T;
+  int64_t blocks_per_row;  // ceil(T / 128)
+  int64_t nblocks;         // B * blocks_per_row
+  int* status;
+};
+
+// v0, v1 -> packed bf16 pairs (v1 in the high half): hi = RN(v), mid = RN(v - hi)
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& mid) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(v1 - h1), "f"(v0 - h0));
+}
+
+__global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const BwdInputTc16Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* ring = smem + H2_SM_G;
+  float* skew = reinterpret_cast<float*>(smem + H2_SM_S);
+  float* outw = reinterpret_cast<float*>(smem + H2_SM_OUT);
+  float* carry = reinterpret_cast<float*>(smem + H2_SM_CARRY);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + H2_SM_BAR);
+  uint64_t* b_full = bars;         // [4]  producers (4 warps) -> issuers
+  uint64_t* b_empty = bars + 4;    // [4]  issuers (2 commits) -> producers
+  uint64_t* d_full = bars + 8;     // [2 buffers][2 column halves]  issuer -> epilogue
+  uint64_t* d_empty = bars + 12;   // [2][2]  epilogue (4 warps) -> issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.bank.C, K = a.bank.K, H = (K - 1) / 2;
+  const int ncb = (C + 15) / 16;  // 16-filter K-steps per tap parity
+  const int Hr = (H + 3) & ~3;    // H rounded up to a multiple of 4: stage columns stay 16-byte aligned in g
+  const int64_t T = a.T;
+
+  // ---------------- setup ------------------------------------------------------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) {
+      tc::mbar_init(&b_full[i], 4);
+      tc::mbar_init(&b_empty[i], 2);
+      tc::mbar_init(&d_full[i], 1);
+      tc::mbar_init(&d_empty[i], 4);
+    }
+    tc::mbar_init_fence();
+  }
+  if (warp == 8) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  for (int i = tid; i < H2_SM_BAR / 16; i += H2_THREADS)
+    reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  {
+    float* wst = reinterpret_cast<float*>(ring);  // fp32 filters [c][256], rows >= C and taps >= K stay zero
+    for (int c = warp; c < C; c += H2_THREADS / 32)
+      synth_filter_warp(a.bank, c, lane, [&](int k, double w) { wst[c * 256 + k] = (float)w; });
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM map: [0,256) two accumulators of 128 columns; [256,320) W' hi, [320,384) W' mid (column = e*32 + c/2)
+  if (warp < 4) {
+    const float* wst = reinterpret_cast<const float*>(ring);
+    const int kp = 32 * warp + lane;  // tap pair = TMEM lane
+    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+#pragma unroll 1
+    for (int e = 0; e < 2; ++e) {
+#pragma unroll 1
+      for (int cg = 0; cg < 4; ++cg) {
+        uint32_t hi[8], mid[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = 16 * cg + 2 * j;
+          split_bf16x2(wst[c * 256 + 2 * kp + e], wst[(c + 1) * 256 + 2 * kp + e], hi[j], mid[j]);
+        }
+        tc::tmem_st8(tmem + lane_base + 256 + 32 * e + 8 * cg, hi);
+        tc::tmem_st8(tmem + lane_base + 320 + 32 * e + 8 * cg, mid);
+      }
+    }
+    tc::tmem_st_wait();
+  }
+  tc::fence_before_sync();
+  __syncthreads();  // the filter staging area becomes the B ring
+  tc::fence_after_sync();
+
+  // ---------------- work: a contiguous range of 128-sample output blocks, cut into per-utterance runs ----------
+  const int64_t v0 = a.nblocks * blockIdx.x / gridDim.x;
+  const int64_t v1 = a.nblocks * (blockIdx.x + 1) / gridDim.x;
+  bool ok = true;
+  int64_t stage = 0;  // global stage counter of this CTA (ring slots / barrier phases)
+
+  int64_t v = v0;
+  while (v < v1) {
+    const int64_t b = v / a.blocks_per_row;
+    const int64_t blk0 = v - b * a.blocks_per_row;
+    int64_t blk1 = blk0 + (v1 - v);
+    if (blk1 > a.blocks_per_row) blk1 = a.blocks_per_row;
+    const int64_t s_out = blk0 * H2_NS;                                   // owned outputs [s_out, e_out)
+    const int64_t e_out = blk1 * H2_NS < T ? blk1 * H2_NS : T;
+    const int64_t c0 = s_out - Hr;  // first D column (position) of the run: a multiple of 4 at or before s_out - H
+    const int nst = (int)((e_out + H + 1 - c0 + H2_NS - 1) / H2_NS);      // columns [s_out - H, e_out + H]
+    v += blk1 - blk0;
+
+    if (warp >= 10) {
+      // ------------- producers: g[:, p] -> bf16 hi/mid -> row (p - col0 + 1) of the slot's planes -----------------
+      // Warp pw owns 32 positions; lane (fg, pg) loads 4 consecutive positions (one LDG.128 per filter) of the
+      // filters [8fg, 8fg+8) and [32+8fg, 32+8fg+8) -- two 16-byte plane rows per position.  The planes fg and
+      // fg+4 are 16 bytes apart modulo 128, so every STS.128 instruction of the warp is conflict-free.
+      const int pw = warp - 10;
+      const int fg = lane >> 3, pg = lane & 7;
+      const int n0 = 32 * pw + 4 * pg;  // first of this thread's four columns within the stage
+      const float* gb = a.g + (b * C) * T;
+      float4 vv[16];
+      auto load_stage = [&](int64_t p) {  // p = position of column n0 (a multiple of 4; T % 4 == 0)
+        const bool in = p >= 0 && p < T;
+        const float* gp = gb + (in ? p : 0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = 8 * fg + (j & 7) + 32 * (j >> 3);
+          vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const float4*>(gp + (int64_t)c * T))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      for (int i = 0; i < nst; ++i) {
+        const int64_t sg = stage + i;
+        const int slot = (int)(sg & 3);
+        // Stage sg-3 complete => slot (sg+1)&3 (the halo target) is free, and so is slot sg&3 (in-order MMAs).
+        if (sg >= 3) ok = tc::mbar_wait(&b_empty[(sg + 1) & 3], (uint32_t)(((sg - 3) >> 2) & 1)) && ok;
+        uint8_t* base = ring + slot * H2_SLOT;
+        if (i == 0) {
+          if (pw == 0) {  // run start: the halo row (position c0 - 1) has no previous stage; lane = filter pair
+            const int64_t p = c0 - 1;
+            const bool in = p >= 0 && p < T;
+            const float w0 = (in && 2 * lane < C) ? __ldg(gb + (int64_t)(2 * lane) * T + p) : 0.f;
+            const float w1 = (in && 2 * lane + 1 < C) ? __ldg(gb + (int64_t)(2 * lane + 1) * T + p) : 0.f;
+            uint32_t h, m;
+            split_bf16x2(w0, w1, h, m);
+            *reinterpret_cast<uint32_t*>(base + (lane >> 2) * H2_PLANE + (lane & 3) * 4) = h;
+            *reinterpret_cast<uint32_t*>(base + (8 + (lane >> 2)) * H2_PLANE + (lane & 3) * 4) = m;
+          }
+          load_stage(c0 + n0);
+        }
+        // the last row of a stage is also the halo row (row 0) of the next stage's slot
+        uint8_t* dup = (pw == 3 && pg == 7 && i + 1 < nst) ? ring + (int)((sg + 1) & 3) * H2_SLOT : nullptr;
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const int cq = fg + 4 * s2;
+          if (cq < 2 * ncb) {
+            const float4* v8 = vv + 8 * s2;
+#pragma unroll
+            for (int o = 0; o < 4; ++o) {
+              auto comp = [&](const float4& f) { return o == 0 ? f.x : o == 1 ? f.y : o == 2 ? f.z : f.w; };
+              uint4 h, m;
+              split_bf16x2(comp(v8[0]), comp(v8[1]), h.x, m.x);
+              split_bf16x2(comp(v8[2]), comp(v8[3]), h.y, m.y);
+              split_bf16x2(comp(v8[4]), comp(v8[5]), h.z, m.z);
+              split_bf16x2(comp(v8[6]), comp(v8[7]), h.w, m.w);
+              uint8_t* dst = base + cq * H2_PLANE + (n0 + o + 1) * 16;
+              *reinterpret_cast<uint4*>(dst) = h;
+              *reinterpret_cast<uint4*>(dst + 8 * H2_PLANE) = m;
+              if (o == 3 && dup) {
+                *reinterpret_cast<uint4*>(dup + cq * H2_PLANE) = h;
+                *reinterpret_cast<uint4*>(dup + (8 + cq) * H2_PLANE) = m;
+              }
+            }
+          }
+        }
+        if (i + 1 < nst) load_stage(c0 + (int64_t)H2_NS * (i + 1) + n0);  // in flight during the next wait
+        tc::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&b_full[slot]);
+      }
+    } else if (warp >= 8) {
+      // ------------- MMA issuers: warp 8 positions 0..63 of the stage, warp 9 positions 64..127 ------------------
+      if (lane == 0) {
+        const int hf = warp - 8;
+        const uint32_t idesc = tc::make_idesc_f16(128, 64, tc::kFmtBF16, tc::kFmtBF16);
+        const uint64_t bdesc = tc::make_smem_desc(H2_PLANE, 128);  // K chunk stride = plane, 8-row groups contiguous
+        for (int i = 0; i < nst; ++i) {
+          const int64_t sg = stage + i;
+          const int slot = (int)(sg & 3), buf = (int)(sg & 1);
+          ok = tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1)) && ok;
+          ok = tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 2) & 1)) && ok;
+          tc::fence_after_sync();
+          const uint32_t d = tmem + 128 * buf + 64 * hf;
+          const uint32_t sbase = tc::smem_addr(ring + slot * H2_SLOT) + hf * 64 * 16;
+          uint32_t acc = 0;
+          for (int e = 0; e < 2; ++e) {
+            uint32_t ah = tmem + 256 + 32 * e;
+            uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
+            for (int cb = 0; cb < ncb; ++cb) {
+              const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
+              tc::mma_f16_ts(d, ah, dh, idesc, acc);
+              tc::mma_f16_ts(d, ah, dm, idesc, 1);
+              tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
+              acc = 1;
+              ah += 8;
+              bh += 2 * H2_PLANE;
+            }
+          }
+          tc::mma_commit(&b_empty[slot]);
+          tc::mma_commit(&d_full[2 * buf + hf]);
+        }
+      }
+      __syncwarp();
+    } else {
+      // ------------- epilogue: TMEM -> skewed column sums -> window -> gx --------------------------------------
+      const int q = warp & 3, hf = warp >> 2;
+      const uint32_t lane_base = (uint32_t)(32 * q) << 16;
+      float* S = skew + warp * H2_SKEW;
+      float* win = outw + warp * 128;
+      float* srow = S + (lane >> 4) * 545 + (lane & 15) * 34;
+      float m0[17], m1[17];
+#pragma unroll
+      for (int m = 0; m < 17; ++m) {
+        m0[m] = (2 * m <= lane) ? 1.f : 0.f;
+        m1[m] = (2 * m >= lane + 3) ? 1.f : 0.f;
+      }
+      tc::named_bar_sync(2, 256);  // previous run's carry writes are done
+      carry[tid] = 0.f;            // new run: nothing carried
+      for (int i = 0; i < nst; ++i) {
+        const int64_t sg = stage + i;
+        const int buf = (int)(sg & 1);
+        const int64_t col0 = c0 + (int64_t)H2_NS * i;  // first position of the stage
+        ok = tc::mbar_wait(&d_full[2 * buf + hf], (uint32_t)((sg >> 1) & 1)) && ok;
+        tc::fence_after_sync();
+        float t1 = 0.f, t2 = 0.f;  // sums for cells 32..63 and 64..95 of the previous chunk (they overlap this one)
+#pragma unroll 1
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t vv[32];
+          tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf + 32 * ch, vv);
+          tc::tmem_ld_wait();
+          if (ch == 1) {  // all 64 columns of this half have left TMEM: release the accumulator
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&d_empty[2 * buf + hf]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) srow[j] = __uint_as_float(vv[j]);
+          __syncwarp();
+          float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
+          const float* col = S + lane;
+#pragma unroll
+          for (int m = 0; m < 17; ++m) {
+            const float u0 = col[32 * m], u1 = col[545 + 32 * m];
+            s00 = fmaf(u0, m0[m], s00);
+            s01 = fmaf(u0, m1[m], s01);
+            s10 = fmaf(u1, m0[m], s10);
+            s11 = fmaf(u1, m1[m], s11);
+          }
+          win[32 * ch + lane] = s00 + t1;
+          t1 = s01 + s10 + t2;
+          t2 = s11;
+          __syncwarp();
+        }
+        win[64 + lane] = t1;
+        win[96 + lane] = t2;
+        // combine the eight windows (warp w starts at cell 64*(q_w + hf_w)) with the carry, fixed order
+        tc::named_bar_sync(2, 256);
+        float tot[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int o = tid + 256 * r;
+          float acc = 0.f;
+          if (o < H2_WIN) {
+            acc = o < 256 ? carry[o] : 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+              const int rel = o - 64 * ((w & 3) + (w >> 2));
+              if (rel >= 0 && rel < 128) acc += outw[w * 128 + rel];
+            }
+          }
+          tot[r] = acc;
+        }
+        tc::named_bar_sync(2, 256);  // everyone has read the old carry and the windows
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int o = tid + 256 * r;
+          if (o < H2_NS) {
+            const int64_t t = col0 - H + o;
+            if (t >= s_out && t < e_out) a.gx[b * T + t] = tot[r];
+          } else if (o < H2_WIN) {
+            carry[o - H2_NS] = tot[r];
+          }
+        }
+      }
+    }
+    stage += nst;
+  }
+  if (!ok && lane == 0) *a.status = 1;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
+  return C <= 64 && K <= 256 && T % 4 == 0 && g_dtype == SINC_DTYPE_F32 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+         di.max_smem_optin >= H2_SM_TOTAL + 1024;
+}
+
+cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, float* gx, int64_t B, int64_t T,
+                                  const DeviceInfo& di, cudaStream_t st) {
+  BwdInputTc16Args a;
+  a.bank = bank;
+  a.g = reinterpret_cast<const float*>(gy);
+  a.gx = gx;
+  a.B = B;
+  a.T = T;
+  a.blocks_per_row = ceil_div64(T, H2_NS);
+  a.nblocks = B * a.blocks_per_row;
+  a.status = tc_status_device_ptr();
+  if (!a.status) return cudaErrorInvalidSymbol;
+  const int grid = (int)(a.nblocks < di.sm_count ? a.nblocks : di.sm_count);
+  const size_t smem = H2_SM_TOTAL + 1024;
+  cudaError_t e = cudaFuncSetAttribute(bwd_input_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bwd_input_tc16_kernel<<<grid, H2_THREADS, smem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace sinc

@@ -62,12 +62,17 @@ __global__ void __launch_bounds__(128, 1) tc_probe_kernel(const ProbeArgs a) {
     tc::fence_after_sync();
   }
   if (tid == 0) {
+    const bool f16 = ((a.idesc >> 7) & 7u) < 2u;  // A format 0/1 = f16/bf16 -> kind::f16, 2 = tf32 -> kind::tf32
     for (int s = 0; s < a.ksteps; ++s) {
       const uint64_t bd = tc::desc_at(a.descB, tc::smem_addr(sB) + s * a.b_step);
-      if (a.a_from_tmem)
-        tc::mma_tf32_ts(tmem, tmem + a_col0 + s * a.a_step, bd, a.idesc, s > 0);
-      else
-        tc::mma_tf32_ss(tmem, tc::desc_at(a.descA, tc::smem_addr(sA) + s * a.a_step), bd, a.idesc, s > 0);
+      if (a.a_from_tmem) {
+        if (f16) tc::mma_f16_ts(tmem, tmem + a_col0 + s * a.a_step, bd, a.idesc, s > 0);
+        else tc::mma_tf32_ts(tmem, tmem + a_col0 + s * a.a_step, bd, a.idesc, s > 0);
+      } else {
+        const uint64_t ad = tc::desc_at(a.descA, tc::smem_addr(sA) + s * a.a_step);
+        if (f16) tc::mma_f16_ss(tmem, ad, bd, a.idesc, s > 0);
+        else tc::mma_tf32_ss(tmem, ad, bd, a.idesc, s > 0);
+      }
     }
     tc::mma_commit(&bar);
   }

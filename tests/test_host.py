@@ -101,6 +101,10 @@ def test_abi_non_compute_calls():
     assert lib.sinc_workspace_bytes(1, 1, 70, 300) > lib.sinc_workspace_bytes(1, 1, 64, 251)
     assert lib.sinc_set_engine(7) == -8
     assert lib.sinc_set_engine(0) == 0 and lib.sinc_get_engine() == 0
+    for code, name in enumerate(("auto", "fma", "tc", "tc_tf32")):      # every engine name the package accepts
+        sb.set_engine(name)
+        assert lib.sinc_get_engine() == code
+    sb.set_engine("auto")
     # argument validation happens before any CUDA call
     fb = _lib.FilterBank()
     assert lib.sinc_forward(ctypes.byref(fb), None, 0, None, 0, 1, 1, None, 0, None) == -1

@@ -20,6 +20,36 @@ def idesc(M, N, a_mn, b_mn):
     return (1 << 4) | (2 << 7) | (2 << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24)
 
 
+def idesc16(M, N, a_fmt, b_fmt):
+    """kind::f16 instruction descriptor: formats 0 = f16, 1 = bf16; fp32 accumulate; both operands K-major."""
+    return (1 << 4) | (a_fmt << 7) | (b_fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24)
+
+
+def to16(mat, fmt):
+    """fp32 array -> uint16 bit patterns of fp16 (fmt 0) or bf16 (fmt 1); the probe data are small integers (exact)."""
+    m = np.ascontiguousarray(mat, dtype=np.float32)
+    if fmt == 0:
+        return m.astype(np.float16).view(np.uint16)
+    return (m.view(np.uint32) >> 16).astype(np.uint16)
+
+
+def pack_words(u16):
+    """uint16 array (even length along the last axis) -> float32 view of the packed 32-bit words."""
+    return np.ascontiguousarray(u16).view(np.uint32).view(np.float32)
+
+
+def kmajor_image16(mat16, lbo, sbo):
+    """mat16 [rows][K] uint16 -> canonical no-swizzle K-major image (16-byte chunks = 8 elements)."""
+    rows, K = mat16.shape
+    size = (rows // 8 - 1) * sbo + (K // 8 - 1) * lbo + 128
+    img = np.zeros(size // 2, dtype=np.uint16)
+    for r in range(rows):
+        for kc in range(K // 8):
+            a = ((r % 8) * 16 + (r // 8) * sbo + kc * lbo) // 2
+            img[a:a + 8] = mat16[r, 8 * kc:8 * kc + 8]
+    return pack_words(img)
+
+
 def kmajor_image(mat, lbo, sbo):
     """mat [rows][K] fp32 -> canonical no-swizzle K-major image: addr(r,kc) = (r%8)*16 + (r//8)*sbo + kc*lbo."""
     rows, K = mat.shape
@@ -73,6 +103,29 @@ def run(case):
         a_from_tmem, a_cols = 1, 8 * ks
         imgB, dB, b_step = x.copy(), smem_desc(16, 128), 32
         idc = idesc(M, N, 0, 0)
+        expect = A @ Bm.T
+    elif case.startswith("h16_"):
+        # kind::f16: case = h16_{ts|ss}_{toep|kmaj}_{a fmt}{b fmt}_n{N}   (fmt: h = fp16, b = bf16)
+        _, mode, blay, fmts, nn = case.split("_")
+        fa, fb = "hb".index(fmts[0]), "hb".index(fmts[1])
+        N, ks = int(nn[1:]), 4
+        Kt = 16 * ks
+        A = ri(M, Kt)
+        if blay == "toep":
+            x = ri(8 * N + Kt + 16)
+            Bm = np.stack([x[8 * n:8 * n + Kt] for n in range(N)])        # B[n,k] = x[8n+k]: row pitch 16 bytes
+            imgB, dB, b_step = pack_words(to16(x, fb)), smem_desc(16, 128), 32
+        else:
+            Bm = ri(N, Kt)
+            lbo, sbo = 128, 128 * (Kt // 8)
+            imgB, dB, b_step = kmajor_image16(to16(Bm, fb), lbo, sbo), smem_desc(lbo, sbo), 256
+        if mode == "ts":
+            imgA, dA, a_step = pack_words(to16(A, fa)).reshape(-1).copy(), 0, 8  # [128][Kt/2] packed words, 8 columns per K-step
+            a_from_tmem, a_cols = 1, Kt // 2
+        else:
+            lbo, sbo = 128, 128 * (Kt // 8)
+            imgA, dA, a_step = kmajor_image16(to16(A, fa), lbo, sbo), smem_desc(lbo, sbo), 256
+        idc = idesc16(M, N, fa, fb)
         expect = A @ Bm.T
     elif case in ("mnmajor_gradfilter", "mnmajor_gradfilter_n256"):
         # D[(c,r), k'] = sum_j g[c, 4j+r] * x[4j+k'];  A MN-major straight from a g tile, B MN-major Toeplitz
@@ -207,12 +260,14 @@ def run(case):
 ALL = ["kmajor_ss", "kmajor_ss_swapped", "toeplitz_b", "toeplitz_b_n128", "toeplitz_b_n256", "tmem_a_toeplitz_b",
        "mnmajor_gradfilter", "mnmajor_gradfilter_n256", "mn_a_dense", "mn_b_dense", "mn_a_gtile", "mn_b_toeplitz",
        "mn_b_toeplitz_lbo16"]
+H16 = ["h16_ss_kmaj_hh_n64", "h16_ts_kmaj_hh_n64", "h16_ts_toep_hh_n128", "h16_ts_toep_bh_n32", "h16_ts_toep_bb_n112",
+       "h16_ts_kmaj_hh_n128", "h16_ss_toep_hh_n256"]
 
 if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[1] == "--one":
         run(sys.argv[2])
     else:
-        for c in (sys.argv[1:] or ALL):
+        for c in (H16 if sys.argv[1:] == ['h16'] else (sys.argv[1:] or ALL)):
             p = subprocess.run([sys.executable, __file__, "--one", c], capture_output=True, text=True, timeout=120)
             out = [l for l in p.stdout.splitlines() if l.startswith("{")]
             print(out[-1] if out else json.dumps({"case": c, "crashed": p.returncode, "stderr": p.stderr[-400:]}), flush=True)
