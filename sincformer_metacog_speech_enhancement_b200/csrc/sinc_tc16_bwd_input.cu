@@ -35,7 +35,9 @@
 
 namespace sinc {
 
-constexpr int H2_THREADS = 448;  // warps 0-7 epilogue (quarter = w%4, column half = w/4), 8-9 issuers, 10-13 producers
+constexpr int H2_THREADS = 512;  // warps 0-7 epilogue (quarter = w%4, column half = w/4), 8-11 producers, 12-13 issuers, 14-15 idle
+constexpr int H2_REGS_WORK = 152;  // setmaxnreg: epilogue and producer warpgroups
+constexpr int H2_REGS_ISSUE = 40;  //             issuer warpgroup (3*128*152 + 128*40 <= 64K)
 constexpr int H2_NS = 128;       // D columns (positions) per stage
 constexpr int H2_SLOTS = 4;      // B ring depth
 constexpr int H2_PLANE = (H2_NS + 1) * 16;       // bytes: halo row + 128 rows of 8 filters x bf16
@@ -43,10 +45,10 @@ constexpr int H2_SLOT = 2 * 8 * H2_PLANE;        // hi planes [8], mid planes [8
 constexpr int H2_WIN = 384;                      // output window of one stage: 128 positions + 2*127 + 1
 constexpr int H2_SKEW = 1092;                    // floats per epilogue warp: 2 regions of 16 rows x pitch 34 (+1)
 constexpr int H2_SM_G = 0;                                     // B ring; in the prologue: fp32 filters [64][256]
-constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // skew buffers
-constexpr int H2_SM_OUT = H2_SM_S + 8 * H2_SKEW * 4;           // 8 x window [128]
-constexpr int H2_SM_CARRY = H2_SM_OUT + 8 * 128 * 4;           // carry [256]
-constexpr int H2_SM_BAR = H2_SM_CARRY + 256 * 4;
+constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // skew buffers: one per (epilogue warp, 32-column chunk)
+constexpr int H2_SM_OUT = H2_SM_S + 8 * 2 * H2_SKEW * 4;       // 2 x 8 x window [128] (double-buffered by stage parity)
+constexpr int H2_SM_CARRY = H2_SM_OUT + 2 * 8 * 128 * 4;       // 2 x carry [256]
+constexpr int H2_SM_BAR = H2_SM_CARRY + 2 * 256 * 4;
 constexpr int H2_SM_TOTAL = H2_SM_BAR + 256;
 static_assert(64 * 256 * 4 <= H2_SLOTS * H2_SLOT, "filter staging must fit in the B ring");
 static_assert(H2_SM_S % 16 == 0 && H2_SM_OUT % 16 == 0, "alignment");
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
     }
     tc::mbar_init_fence();
   }
-  if (warp == 8) {
+  if (warp == 12) {
     tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
@@ -139,41 +141,51 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
   tc::fence_after_sync();
 
   // ---------------- work: a contiguous range of 128-sample output blocks, cut into per-utterance runs ----------
+  // Every role walks the same sequence of (run, stage) pairs.  The three roles are separate top-level branches
+  // that never merge before the end of the kernel, so each keeps the register budget setmaxnreg gave it.
   const int64_t v0 = a.nblocks * blockIdx.x / gridDim.x;
   const int64_t v1 = a.nblocks * (blockIdx.x + 1) / gridDim.x;
   bool ok = true;
-  int64_t stage = 0;  // global stage counter of this CTA (ring slots / barrier phases)
+  auto for_each_run = [&](auto&& body) {
+    int64_t stage = 0;  // global stage counter of this CTA (ring slots / barrier phases)
+    int64_t v = v0;
+    while (v < v1) {
+      const int64_t b = v / a.blocks_per_row;
+      const int64_t blk0 = v - b * a.blocks_per_row;
+      int64_t blk1 = blk0 + (v1 - v);
+      if (blk1 > a.blocks_per_row) blk1 = a.blocks_per_row;
+      const int64_t s_out = blk0 * H2_NS;                                   // owned outputs [s_out, e_out)
+      const int64_t e_out = blk1 * H2_NS < T ? blk1 * H2_NS : T;
+      const int64_t c0 = s_out - Hr;  // first D column (position) of the run: a multiple of 4 at or before s_out - H
+      const int nst = (int)((e_out + H + 1 - c0 + H2_NS - 1) / H2_NS);      // columns [s_out - H, e_out + H]
+      v += blk1 - blk0;
+      body(b, s_out, e_out, c0, nst, stage);
+      stage += nst;
+    }
+  };
 
-  int64_t v = v0;
-  while (v < v1) {
-    const int64_t b = v / a.blocks_per_row;
-    const int64_t blk0 = v - b * a.blocks_per_row;
-    int64_t blk1 = blk0 + (v1 - v);
-    if (blk1 > a.blocks_per_row) blk1 = a.blocks_per_row;
-    const int64_t s_out = blk0 * H2_NS;                                   // owned outputs [s_out, e_out)
-    const int64_t e_out = blk1 * H2_NS < T ? blk1 * H2_NS : T;
-    const int64_t c0 = s_out - Hr;  // first D column (position) of the run: a multiple of 4 at or before s_out - H
-    const int nst = (int)((e_out + H + 1 - c0 + H2_NS - 1) / H2_NS);      // columns [s_out - H, e_out + H]
-    v += blk1 - blk0;
-
-    if (warp >= 10) {
+  if (warp >= 8 && warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(H2_REGS_WORK));
+    for_each_run([&](int64_t b, int64_t s_out, int64_t e_out, int64_t c0, int nst, int64_t stage) {
+      (void)s_out; (void)e_out;
       // ------------- producers: g[:, p] -> bf16 hi/mid -> row (p - col0 + 1) of the slot's planes -----------------
       // Warp pw owns 32 positions; lane (fg, pg) loads 4 consecutive positions (one LDG.128 per filter) of the
-      // filters [8fg, 8fg+8) and [32+8fg, 32+8fg+8) -- two 16-byte plane rows per position.  The planes fg and
-      // fg+4 are 16 bytes apart modulo 128, so every STS.128 instruction of the warp is conflict-free.
-      const int pw = warp - 10;
-      const int fg = lane >> 3, pg = lane & 7;
+      // filters [8fg, 8fg+8) and [32+8fg, 32+8fg+8) -- two 16-byte plane rows per position.  Neighbouring planes
+      // are 16 bytes apart modulo 128 and lane = 4*pg + fg, so every quarter-warp of an STS.128 covers 8 distinct
+      // 16-byte bank groups: conflict-free.
+      const int pw = warp - 8;
+      const int fg = lane & 3, pg = lane >> 2;  // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups
       const int n0 = 32 * pw + 4 * pg;  // first of this thread's four columns within the stage
       const float* gb = a.g + (b * C) * T;
       float4 vv[16];
       auto load_stage = [&](int64_t p) {  // p = position of column n0 (a multiple of 4; T % 4 == 0)
         const bool in = p >= 0 && p < T;
-        const float* gp = gb + (in ? p : 0);
+        const float* q = gb + (in ? p : 0) + (int64_t)(8 * fg) * T;  // one running row pointer: no address array
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int c = 8 * fg + (j & 7) + 32 * (j >> 3);
-          vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const float4*>(gp + (int64_t)c * T))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          q += (j == 7) ? 25 * T : T;
         }
       };
       for (int i = 0; i < nst; ++i) {
@@ -225,10 +237,14 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&b_full[slot]);
       }
-    } else if (warp >= 8) {
-      // ------------- MMA issuers: warp 8 positions 0..63 of the stage, warp 9 positions 64..127 ------------------
-      if (lane == 0) {
-        const int hf = warp - 8;
+    });
+  } else if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(H2_REGS_ISSUE));
+    for_each_run([&](int64_t b, int64_t s_out, int64_t e_out, int64_t c0, int nst, int64_t stage) {
+      (void)b; (void)s_out; (void)e_out; (void)c0;
+      // ------------- MMA issuers: warp 12 positions 0..63 of the stage, warp 13 positions 64..127 ----------------
+      if (lane == 0 && warp < 14) {
+        const int hf = warp - 12;
         const uint32_t idesc = tc::make_idesc_f16(128, 64, tc::kFmtBF16, tc::kFmtBF16);
         const uint64_t bdesc = tc::make_smem_desc(H2_PLANE, 128);  // K chunk stride = plane, 8-row groups contiguous
         for (int i = 0; i < nst; ++i) {
@@ -258,94 +274,94 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         }
       }
       __syncwarp();
-    } else {
+    });
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(H2_REGS_WORK));
+    for_each_run([&](int64_t b, int64_t s_out, int64_t e_out, int64_t c0, int nst, int64_t stage) {
       // ------------- epilogue: TMEM -> skewed column sums -> window -> gx --------------------------------------
       const int q = warp & 3, hf = warp >> 2;
       const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-      float* S = skew + warp * H2_SKEW;
-      float* win = outw + warp * 128;
-      float* srow = S + (lane >> 4) * 545 + (lane & 15) * 34;
+      float* S0 = skew + warp * (2 * H2_SKEW);  // chunk 0 (columns 0..31 of this warp's half), chunk 1 follows
+      float* srow = S0 + (lane >> 4) * 545 + (lane & 15) * 34;
       float m0[17], m1[17];
 #pragma unroll
       for (int m = 0; m < 17; ++m) {
         m0[m] = (2 * m <= lane) ? 1.f : 0.f;
         m1[m] = (2 * m >= lane + 3) ? 1.f : 0.f;
       }
-      tc::named_bar_sync(2, 256);  // previous run's carry writes are done
-      carry[tid] = 0.f;            // new run: nothing carried
+      tc::named_bar_sync(2, 256);  // previous run's carry traffic is done
+      carry[tid] = 0.f;            // new run: nothing carried (stage 0 reads carry buffer 0)
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
-        const int buf = (int)(sg & 1);
+        const int buf = (int)(sg & 1), cb = i & 1;
         const int64_t col0 = c0 + (int64_t)H2_NS * i;  // first position of the stage
         ok = tc::mbar_wait(&d_full[2 * buf + hf], (uint32_t)((sg >> 1) & 1)) && ok;
         tc::fence_after_sync();
-        float t1 = 0.f, t2 = 0.f;  // sums for cells 32..63 and 64..95 of the previous chunk (they overlap this one)
-#pragma unroll 1
-        for (int ch = 0; ch < 2; ++ch) {
-          uint32_t vv[32];
-          tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf + 32 * ch, vv);
-          tc::tmem_ld_wait();
-          if (ch == 1) {  // all 64 columns of this half have left TMEM: release the accumulator
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&d_empty[2 * buf + hf]);
-          }
+        uint32_t va[32], vb[32];
+        tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf, va);
+        tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf + 32, vb);
+        tc::tmem_ld_wait();
+        tc::fence_before_sync();  // all 64 columns of this half have left TMEM: release the accumulator
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&d_empty[2 * buf + hf]);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) srow[j] = __uint_as_float(vv[j]);
-          __syncwarp();
-          float s00 = 0.f, s01 = 0.f, s10 = 0.f, s11 = 0.f;
-          const float* col = S + lane;
-#pragma unroll
-          for (int m = 0; m < 17; ++m) {
-            const float u0 = col[32 * m], u1 = col[545 + 32 * m];
-            s00 = fmaf(u0, m0[m], s00);
-            s01 = fmaf(u0, m1[m], s01);
-            s10 = fmaf(u1, m0[m], s10);
-            s11 = fmaf(u1, m1[m], s11);
-          }
-          win[32 * ch + lane] = s00 + t1;
-          t1 = s01 + s10 + t2;
-          t2 = s11;
-          __syncwarp();
+        for (int j = 0; j < 32; ++j) {
+          srow[j] = __uint_as_float(va[j]);
+          srow[H2_SKEW + j] = __uint_as_float(vb[j]);
         }
-        win[64 + lane] = t1;
-        win[96 + lane] = t2;
-        // combine the eight windows (warp w starts at cell 64*(q_w + hf_w)) with the carry, fixed order
+        __syncwarp();
+        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+        const float* col = S0 + lane;
+#pragma unroll
+        for (int m = 0; m < 17; ++m) {
+          const float u0 = col[32 * m], u1 = col[545 + 32 * m];
+          const float w0 = col[H2_SKEW + 32 * m], w1 = col[H2_SKEW + 545 + 32 * m];
+          a00 = fmaf(u0, m0[m], a00);
+          a01 = fmaf(u0, m1[m], a01);
+          a10 = fmaf(u1, m0[m], a10);
+          a11 = fmaf(u1, m1[m], a11);
+          b00 = fmaf(w0, m0[m], b00);
+          b01 = fmaf(w0, m1[m], b01);
+          b10 = fmaf(w1, m0[m], b10);
+          b11 = fmaf(w1, m1[m], b11);
+        }
+        // chunk 0 covers window cells [0,96): a00 | a01 + a10 | a11; chunk 1 the same 32 cells later
+        float* win = outw + buf * (8 * 128) + warp * 128;
+        win[lane] = a00;
+        win[32 + lane] = (a01 + a10) + b00;
+        win[64 + lane] = a11 + (b01 + b10);
+        win[96 + lane] = b11;
+        // One barrier per stage: windows and carry are double-buffered, so the reads below cannot race with the
+        // next stage's writes (those come after the next barrier, which every thread passes after these reads).
         tc::named_bar_sync(2, 256);
-        float tot[2];
+        const float* wbase = outw + buf * (8 * 128);
+        const float* cin = carry + cb * 256;
+        float* cout = carry + (cb ^ 1) * 256;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const int o = tid + 256 * r;
-          float acc = 0.f;
           if (o < H2_WIN) {
-            acc = o < 256 ? carry[o] : 0.f;
+            float acc = o < 256 ? cin[o] : 0.f;
 #pragma unroll
-            for (int w = 0; w < 8; ++w) {
+            for (int w = 0; w < 8; ++w) {  // warp w's window starts at cell 64*(q_w + hf_w); fixed order
               const int rel = o - 64 * ((w & 3) + (w >> 2));
-              if (rel >= 0 && rel < 128) acc += outw[w * 128 + rel];
+              if (rel >= 0 && rel < 128) acc += wbase[w * 128 + rel];
             }
-          }
-          tot[r] = acc;
-        }
-        tc::named_bar_sync(2, 256);  // everyone has read the old carry and the windows
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int o = tid + 256 * r;
-          if (o < H2_NS) {
-            const int64_t t = col0 - H + o;
-            if (t >= s_out && t < e_out) a.gx[b * T + t] = tot[r];
-          } else if (o < H2_WIN) {
-            carry[o - H2_NS] = tot[r];
+            if (o < H2_NS) {
+              const int64_t t = col0 - H + o;
+              if (t >= s_out && t < e_out) a.gx[b * T + t] = acc;
+            } else {
+              cout[o - H2_NS] = acc;
+            }
           }
         }
       }
-    }
-    stage += nst;
+    });
   }
   if (!ok && lane == 0) *a.status = 1;
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == 12) tc::tmem_dealloc(tmem, 512);
 }
 
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
