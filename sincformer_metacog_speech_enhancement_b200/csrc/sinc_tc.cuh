@@ -143,11 +143,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must end in a wrong answer (caught by the parity tests), never in a hung GPU.
-// try_wait itself suspends for a hardware time slice, so the bound is of the order of seconds.
+// The bound is one second of wall time (%globaltimer); callers short-circuit (`ok = ok && mbar_wait(..)`) so a
+// role that has timed out once stops waiting and the kernel drains within a couple of seconds.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 22); ++spin)
-    if (mbar_try_wait(bar, parity)) return true;
-  return false;
+  if (mbar_try_wait(bar, parity)) return true;
+  const uint64_t t0 = global_timer_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int spin = 0; spin < 64; ++spin)
+      if (mbar_try_wait(bar, parity)) return true;
+    if (global_timer_ns() - t0 > 1000000000ull) return false;
+  }
 }
 
 // ---- 1-D bulk copies (TMA engine, no tensor map) -------------------------------------------------------

@@ -36,8 +36,10 @@
 namespace sinc {
 
 constexpr int H2_THREADS = 512;  // warps 0-7 epilogue (quarter = w%4, column half = w/4), 8-11 producers, 12-13 issuers, 14-15 idle
-constexpr int H2_REGS_WORK = 152;  // setmaxnreg: epilogue and producer warpgroups
-constexpr int H2_REGS_ISSUE = 40;  //             issuer warpgroup (3*128*152 + 128*40 <= 64K)
+// setmaxnreg re-partitions the registers the CTA was LAUNCHED with (512 threads x 128), not the whole file:
+constexpr int H2_REGS_WORK = 152;  // epilogue and producer warpgroups
+constexpr int H2_REGS_ISSUE = 40;  // issuer warpgroup
+static_assert(3 * 128 * H2_REGS_WORK + 128 * H2_REGS_ISSUE <= H2_THREADS * 128, "setmaxnreg.inc would block forever");
 constexpr int H2_NS = 128;       // D columns (positions) per stage
 constexpr int H2_SLOTS = 4;      // B ring depth
 constexpr int H2_PLANE = (H2_NS + 1) * 16;       // bytes: halo row + 128 rows of 8 filters x bf16
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         const int64_t sg = stage + i;
         const int slot = (int)(sg & 3);
         // Stage sg-3 complete => slot (sg+1)&3 (the halo target) is free, and so is slot sg&3 (in-order MMAs).
-        if (sg >= 3) ok = tc::mbar_wait(&b_empty[(sg + 1) & 3], (uint32_t)(((sg - 3) >> 2) & 1)) && ok;
+        if (sg >= 3) ok = ok && tc::mbar_wait(&b_empty[(sg + 1) & 3], (uint32_t)(((sg - 3) >> 2) & 1));
         uint8_t* base = ring + slot * H2_SLOT;
         if (i == 0) {
           if (pw == 0) {  // run start: the halo row (position c0 - 1) has no previous stage; lane = filter pair
@@ -250,8 +252,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         for (int i = 0; i < nst; ++i) {
           const int64_t sg = stage + i;
           const int slot = (int)(sg & 3), buf = (int)(sg & 1);
-          ok = tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1)) && ok;
-          ok = tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 2) & 1)) && ok;
+          ok = ok && tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1));
+          ok = ok && tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 2) & 1));
           tc::fence_after_sync();
           const uint32_t d = tmem + 128 * buf + 64 * hf;
           const uint32_t sbase = tc::smem_addr(ring + slot * H2_SLOT) + hf * 64 * 16;
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         const int64_t sg = stage + i;
         const int buf = (int)(sg & 1), cb = i & 1;
         const int64_t col0 = c0 + (int64_t)H2_NS * i;  // first position of the stage
-        ok = tc::mbar_wait(&d_full[2 * buf + hf], (uint32_t)((sg >> 1) & 1)) && ok;
+        ok = ok && tc::mbar_wait(&d_full[2 * buf + hf], (uint32_t)((sg >> 1) & 1));
         tc::fence_after_sync();
         uint32_t va[32], vb[32];
         tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf, va);

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
             const int64_t kc = kc0 + qfirst + 2 * (i0 + u);
             const int s = (int)(kc % GF_RING);
             const uint32_t par = (uint32_t)((kc / GF_RING) & 1);
-            ok = tc::mbar_wait(&a_empty[s], par ^ 1) && ok;
+            ok = ok && tc::mbar_wait(&a_empty[s], par ^ 1);
             tc::fence_after_sync();
             const float v[8] = {cur[2 * u].x, cur[2 * u].y, cur[2 * u].z, cur[2 * u].w,
                                 cur[2 * u + 1].x, cur[2 * u + 1].y, cur[2 * u + 1].z, cur[2 * u + 1].w};
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
       const bool flush_now = ((it + 1) % GF_FLUSH == 0) || (it + 1 == my_tiles);
       if (flush_now && grp == 0) {
         const uint32_t fpar = (uint32_t)((it / GF_FLUSH) & 1);
-        ok = tc::mbar_wait(d_full, fpar) && ok;
+        ok = ok && tc::mbar_wait(d_full, fpar);
         tc::fence_after_sync();
 #pragma unroll 1
         for (int ch = 0; ch < GF_DCOLS / 32; ++ch) {
@@ -220,10 +220,10 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
         const int64_t left = T - tb;
         const int nq = (int)((left < GF_XSTAGE ? left : GF_XSTAGE) + 15) / 16;
         const int xb = (int)(it & 1);
-        ok = tc::mbar_wait(&x_full[xb], (uint32_t)((it >> 1) & 1)) && ok;
+        ok = ok && tc::mbar_wait(&x_full[xb], (uint32_t)((it >> 1) & 1));
         if (it % GF_FLUSH == 0 && it > 0) {
           // accumulators were handed to the flusher after tile it-1: wait until they have been read out
-          ok = tc::mbar_wait(d_empty, (uint32_t)(((it / GF_FLUSH) - 1) & 1)) && ok;
+          ok = ok && tc::mbar_wait(d_empty, (uint32_t)(((it / GF_FLUSH) - 1) & 1));
           acc = 0;
         }
         const uint32_t xbase = tc::smem_addr(xs + (size_t)xb * 8 * GF_XLEN);
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
         uint64_t bl = tc::desc_at(bdesc, xbase + (2 * rho + 1) * GF_XLEN * 4);
         for (int q = 0; q < nq; ++q) {
           const int s = (int)(kc % GF_RING);
-          ok = tc::mbar_wait(&a_full[s], (uint32_t)((kc / GF_RING) & 1)) && ok;
+          ok = ok && tc::mbar_wait(&a_full[s], (uint32_t)((kc / GF_RING) & 1));
           tc::fence_after_sync();
           const uint32_t ah = tmem + GF_DCOLS + 16 * s, al = ah + 8;
           tc::mma_tf32_ts(d, ah, bh, idesc, acc);
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(GF_THREADS, 1) bwd_filter_tc_kernel(const BwdF
         const int64_t t = tb - H + lane + 32 * r;
         v[r] = (t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
       }
-      ok = tc::mbar_wait(&x_empty[xb], (uint32_t)(((it >> 1) & 1) ^ 1)) && ok;
+      ok = ok && tc::mbar_wait(&x_empty[xb], (uint32_t)(((it >> 1) & 1) ^ 1));
       float* base = xs + (size_t)xb * 8 * GF_XLEN;
 #pragma unroll
       for (int r = 0; r < NV; ++r) {

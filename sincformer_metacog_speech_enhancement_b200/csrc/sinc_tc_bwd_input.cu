@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
         const int sa = (int)(sg & 1);
-        ok = tc::mbar_wait(&a_empty[sa], (uint32_t)(((sg >> 1) & 1) ^ 1)) && ok;
+        ok = ok && tc::mbar_wait(&a_empty[sa], (uint32_t)(((sg >> 1) & 1) ^ 1));
         tc::fence_after_sync();
         const uint32_t dst = tmem + lane_base + 256 + 128 * sa;
 #pragma unroll
@@ -167,8 +167,8 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
         for (int i = 0; i < nst; ++i) {
           const int64_t sg = stage + i;
           const int sa = (int)(sg & 1);
-          ok = tc::mbar_wait(&d_empty[hf], (uint32_t)((sg & 1) ^ 1)) && ok;
-          ok = tc::mbar_wait(&a_full[sa], (uint32_t)((sg >> 1) & 1)) && ok;
+          ok = ok && tc::mbar_wait(&d_empty[hf], (uint32_t)((sg & 1) ^ 1));
+          ok = ok && tc::mbar_wait(&a_full[sa], (uint32_t)((sg >> 1) & 1));
           tc::fence_after_sync();
           uint32_t ah = tmem + 256 + 128 * sa;
           uint64_t bh = bh0, bl = bl0;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(GI_THREADS, 1) bwd_input_tc_kernel(const BwdIn
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
         const int64_t c0 = s_out - H + (int64_t)GI_NS * i;  // first position of the stage
-        ok = tc::mbar_wait(&d_full[hf], (uint32_t)(sg & 1)) && ok;
+        ok = ok && tc::mbar_wait(&d_full[hf], (uint32_t)(sg & 1));
         tc::fence_after_sync();
         float tail = 0.f;  // column sums of the upper 32 rows of the previous chunk (they overlap the next chunk)
 #pragma unroll 1

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) fwd_tc_kernel(const FwdTcArgs a
         const int64_t t = t0 - H + lane + 32 * r;
         v[r] = (t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
       }
-      ok = tc::mbar_wait(&x_empty[buf], par ^ 1) && ok;
+      ok = ok && tc::mbar_wait(&x_empty[buf], par ^ 1);
       float* xh = xbuf + (2 * buf) * TF_XT;
       float* xl = xh + TF_XT;
 #pragma unroll
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(TF_THREADS, 1) fwd_tc_kernel(const FwdTcArgs a
       const uint64_t bl0 = tc::desc_at(bdesc, xh_addr + TF_XT * 4);
       for (int64_t it = buf; it < my_tiles; it += 2) {
         const uint32_t par = (uint32_t)((it >> 1) & 1);
-        ok = tc::mbar_wait(&acc_empty[buf], par ^ 1) && ok;
-        ok = tc::mbar_wait(&x_full[buf], par) && ok;
+        ok = ok && tc::mbar_wait(&acc_empty[buf], par ^ 1);
+        ok = ok && tc::mbar_wait(&x_full[buf], par);
         tc::fence_after_sync();
         uint64_t bh = bh0, bl = bl0, al = adesc0;
         uint32_t ah = tmem + 256;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) fwd_tc_kernel(const FwdTcArgs a
       const int64_t t0 = (tile - b * a.tiles_per_row) * TF_TT;
       if (lane < 8) tc::bulk_wait_read<0>();   // staging rows of the previous tile have been read out
       tc::named_bar_sync(1, 128);
-      ok = tc::mbar_wait(&acc_full[buf], par) && ok;
+      ok = ok && tc::mbar_wait(&acc_full[buf], par);
       tc::fence_after_sync();
       const uint32_t d = tmem + lane_base + (uint32_t)(buf * TF_NJ);
 #pragma unroll 1

@@ -5,7 +5,10 @@ mkdir -p gpurun_out
 TAG=${1:-r01n}
 KREGEX=${2:-tc_kernel}
 NCAP=${3:-3}
-timeout 900 python -m pytest tests -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"
+# pre-flight: one small backward on the tensor-core engine under a short timeout -- a protocol bug must not eat the budget
+timeout 150 python -m pytest tests/test_gpu_tc.py -q -m gpu -x -k "backward and 1000" > gpurun_out/${TAG}_preflight.log 2>&1
+rc=$?; echo "preflight exit $rc"; if [ $rc -ne 0 ]; then tail -30 gpurun_out/${TAG}_preflight.log; exit 1; fi
+timeout 600 python -m pytest tests -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"
 grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/${TAG}_pytest.log | head -20; grep -E "^E  " gpurun_out/${TAG}_pytest.log | head -20
 timeout 600 python bench.py --no-cpu > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
 python - <<PY
