@@ -48,6 +48,8 @@ WorkspaceLayout workspace_layout(int C, int K) {
   wl.partial_bytes = (size_t)kMaxPartialSlots * wl.Cpad * wl.Kpad * sizeof(float);
   const size_t tc_bytes = tc_bwd_filter_partial_bytes(C);
   if (tc_bytes > wl.partial_bytes) wl.partial_bytes = tc_bytes;
+  const size_t tc16_bytes = tc16_bwd_filter_partial_bytes(C);
+  if (tc16_bytes > wl.partial_bytes) wl.partial_bytes = tc16_bytes;
   wl.total_bytes = (wl.partial_bytes + 255) / 256 * 256 + 256;
   return wl;
 }
@@ -198,16 +200,23 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     float* partials = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
     int slots = 0;
     const bool tc_ok = tc_bwd_filter_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
-    const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
-                                  (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter));
-    if (use_tc)
+    const bool tc16_ok = tc16_bwd_filter_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
+    const bool want_tc = engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
+                         (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter);
+    const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
+    const bool use_tc = want_tc && tc_ok && !use_tc16;
+    if (use_tc16)
+      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
+    else if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else
       e = launch_bwd_filter_fma(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
     if (e != cudaSuccess) return (int)e;
-    e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, use_tc ? 1 : 0, grad_low, grad_band, grad_filters, st);
+    e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, use_tc16 ? 2 : use_tc ? 1 : 0, grad_low, grad_band,
+                        grad_filters, st);
     if (e != cudaSuccess) return (int)e;
-    mask |= use_tc ? 4 : 0;
+    mask |= (use_tc || use_tc16) ? 4 : 0;
+    mask |= use_tc16 ? 32 : 0;
   }
   t_last_mask.store((t_last_mask.load() & 1) | mask);
   return 0;

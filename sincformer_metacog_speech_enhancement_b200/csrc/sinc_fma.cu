@@ -521,7 +521,9 @@ __device__ __forceinline__ double block_sum(double v, double* scratch) {
 __device__ __forceinline__ double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
 
 // layout 0: FMA partial tiles [slot][Cpad][Kpad];  layout 1: tcgen05 partial tiles [slot][nblk][128][320] with
-// row (c_local, h) and column rho*80 + n holding tap k = 4n + rho - 8h (sinc_tc_bwd_filter.cu)
+// row (c_local, h) and column rho*80 + n holding tap k = 4n + rho - 8h (sinc_tc_bwd_filter.cu);  layout 2: 16-bit
+// tcgen05 partial tiles [slot][nblk][128][128], row (c_local, h), column rho*32 + n holding the single tap
+// k = 8n + rho + 4h (sinc_tc16_bwd_filter.cu)
 __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, const float* __restrict__ partials,
                                                               int slots, int Cpad, int Kpad, int layout,
                                                               float* grad_low, float* grad_band,
@@ -543,6 +545,13 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
         const float* p = partials + (size_t)c * Kpad + k;
 #pragma unroll 4
         for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * Cpad * Kpad);
+      } else if (layout == 2) {
+        const int nblk = Cpad / 64;
+        const size_t slot_stride = (size_t)nblk * 128 * 128;
+        const int h = (k >> 2) & 1, rho = k & 3, n = k >> 3;
+        const float* p = partials + ((size_t)(c / 64) * 128 + 2 * (c % 64) + h) * 128 + rho * 32 + n;
+#pragma unroll 4
+        for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * slot_stride);
       } else {
         const int nblk = Cpad / 64;
         const size_t slot_stride = (size_t)nblk * 128 * 320;

@@ -34,6 +34,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, int a_mn_ma
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- warp-uniform MMA issue -----------------------------------------------------------------------------
+// tcgen05.mma takes its descriptors from uniform registers.  Inside `if (lane == 0)` nothing is warp-uniform for
+// the compiler, so every operand of every MMA goes through ELECT + R2UR (~100 cycles per instruction, ncu r01v).
+// Issuer warps therefore run their loops with ALL lanes (uniform control flow, uniform values) and predicate only
+// the tcgen05 instructions on the elected lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // ---- TMEM allocation (whole-warp, .sync.aligned) -------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(dst_smem)),
@@ -183,6 +195,10 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
                    smem_addr(sdst)),
                "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
+}
+// L2 prefetch of a contiguous global range (no destination, no completion tracking): bytes % 16 == 0, 16-byte aligned
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");

@@ -1,0 +1,433 @@
+// tcgen05 engine, grad-filter, 16-bit split operands:
+//     G[c,k] = sum_b sum_t g[b,c,t] x[b,t+k-H]                          (ConvolutionBackward0, grad-weight)
+// bf16 hi/mid split (three kind::f16 MMAs per product, fp32 accumulate), sm_100a only.
+// Output: partial tiles for finalize_kernel (layout 2).
+//
+// Precision: 16 significant bits per operand, ~5e-6 max-norm relative on G against the fp64 oracle (gate 1e-4);
+// the 3xTF32 kernel (sinc_tc_bwd_filter.cu) stays available as SINC_ENGINE_TC_TF32.
+//
+// Formulation.  The contraction runs over time, 16 samples per K-step.  The B operand is the waveform read IN
+// PLACE through a Toeplitz descriptor (a K-major no-swizzle operand with LBO = 16, SBO = 128 is a matrix with a
+// row pitch of 16 bytes = 8 bf16 samples):  B_rho[n, kappa] = xs_rho[8n + kappa + 16q],  xs_rho[i] = x[tb-H+i+rho],
+// four copies shifted by rho = 0..3 samples so that every start address stays 16-byte aligned.  Row (c,h) of the
+// A operand holds the 16 samples g[c, tb + 16q - 4h + kappa], h = 0,1 -- two time interleaves per filter give
+// M = 128 rows from 64 filters -- and then
+//     D_rho[(c,h), n]  accumulates  G[c, k]  with  k = 8n + rho + 4h :
+// the interleave offset of 4 samples makes the two rows of a filter produce COMPLEMENTARY taps (k mod 8 in 0..3
+// and 4..7), so four shifts x N = 32 columns cover K <= 256 taps with no redundant MMA work (the 3xTF32 kernel
+// computes every tap in both interleaves: 78 % useful).  Each g sample is converted twice (once per interleave).
+//
+// A (= grad_y) is staged as raw fp32 rows by 1-D bulk copies (4 stages x 64 rows x 128 samples in flight), read back
+// row-per-lane, split into bf16 hi/mid and written with tcgen05.st into an 8-deep TMEM ring; every MMA is the TS
+// form (A from TMEM), the B tiles are 1 KB each.
+//     TMEM  two accumulator sets [0,128) / [128,256): D_rho = 32 columns  |  A ring [256,384): 16 columns per K-step
+//     SMEM  grad_y staging ring 136 KB  |  2 x 4 x (hi,mid) shifted waveform tiles, 25 KB
+// The accumulators are double-buffered: while one set is flushed (read-modify-write of the CTA's own partial tile in
+// the workspace, every F2_FLUSH tiles) the MMAs of the next window run into the other.
+#include <cuda_bf16.h>
+
+#include "sinc_internal.h"
+#include "sinc_tc.cuh"
+
+namespace sinc {
+
+constexpr int F2_THREADS = 512;  // warps 0-7 grad_y converters (2 groups), 8-9 MMA issuers, 10 waveform producer,
+                                 // 11 grad_y bulk-copy issuer, 12-15 flush
+constexpr int F2_N = 32;                    // MMA N (tap columns per shift rho)
+constexpr int F2_TILE = 512;                // samples per tile = 32 K-steps of 16 samples
+constexpr int F2_XLEN = 784;                // bf16 elements per shifted waveform copy: 8*31 + 16*33 + 8 rounded up
+constexpr int F2_RING = 8;                  // TMEM A ring depth (K-steps)
+constexpr int F2_FLUSH = 8;                 // tiles per accumulation window (4096 samples)
+constexpr int F2_DCOLS = 4 * F2_N;          // 128
+constexpr int F2_GSAMP = 128;               // samples per grad_y staging stage (8 K-steps)
+constexpr int F2_GPITCH = F2_GSAMP * 4 + 32;  // bytes per staged row: 32 mod 128, so the row-per-lane LDS.128 of a
+                                              // quarter-warp (4 filters x 2 interleaves) hit 8 distinct bank groups
+constexpr int F2_GSTAGES = 4;               // staging ring depth: 128 KB of grad_y in flight per SM
+constexpr int F2_GSTAGE_BYTES = 64 * F2_GPITCH;
+constexpr int F2_SM_G = 0;                  // [F2_GSTAGES][64 rows][F2_GPITCH]
+constexpr int F2_SM_X = F2_SM_G + F2_GSTAGES * F2_GSTAGE_BYTES;  // [buf 2][rho 4][hi/mid 2][F2_XLEN] bf16
+constexpr int F2_SM_BAR = F2_SM_X + 2 * 8 * F2_XLEN * 2;
+constexpr int F2_SM_TOTAL = F2_SM_BAR + 256;
+static_assert((F2_XLEN * 2) % 16 == 0, "waveform copies must stay 16-byte aligned");
+
+struct BwdFilterTc16Args {
+  const float* x;
+  int64_t xsb;
+  const float* g;
+  int64_t B, T;
+  int C, K;
+  float* partials;  // [gridDim.x / nblk][nblk][128][F2_DCOLS]
+  int nblk;         // filter blocks of 64
+  int64_t tiles_per_row;
+  int64_t ntiles;
+  int* status;
+};
+
+__device__ __forceinline__ void f2_split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& mid) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  const float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(v1 - h1), "f"(v0 - h0));
+}
+
+// K-steps of a tile: the h = 1 interleave lags by 4 samples, so the last tile of an utterance needs the step that
+// covers its final 4 samples.
+__device__ __forceinline__ int f2_ksteps(int64_t left, bool last) {
+  const int span = (int)(left < F2_TILE ? left : F2_TILE) + (last ? 4 : 0);
+  return (span + 15) / 16;
+}
+
+__global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const BwdFilterTc16Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint16_t* xs = reinterpret_cast<uint16_t*>(smem + F2_SM_X);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_SM_BAR);
+  uint64_t* a_full = bars;            // [F2_RING]  producers (4 warps of one group) -> issuers
+  uint64_t* a_empty = bars + 8;       // [F2_RING]  issuers (2 commits) -> producers
+  uint64_t* x_full = bars + 16;       // [2]
+  uint64_t* x_empty = bars + 18;      // [2]  issuers (2 commits)
+  uint64_t* d_full = bars + 20;       // [2]  issuers (2 commits) -> flush warps
+  uint64_t* d_empty = bars + 22;      // [2]  flush warps (4) -> issuers
+  uint64_t* g_full = bars + 24;       // [F2_GSTAGES]  bulk copies (expect_tx) -> converters
+  uint64_t* g_empty = bars + 28;      // [F2_GSTAGES]  converters (8 warps) -> copy issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint8_t* gst = smem + F2_SM_G;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.C, H = (a.K - 1) / 2;
+  const int per_blk = gridDim.x / a.nblk;
+  const int fblk = blockIdx.x % a.nblk;
+  const int slot = blockIdx.x / a.nblk;
+  const int c0 = fblk * 64;
+  const int64_t T = a.T;
+
+  if (tid == 0) {
+    for (int i = 0; i < F2_RING; ++i) {
+      tc::mbar_init(&a_full[i], 4);
+      tc::mbar_init(&a_empty[i], 2);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&x_full[i], 1);
+      tc::mbar_init(&x_empty[i], 2);
+      tc::mbar_init(&d_full[i], 2);
+      tc::mbar_init(&d_empty[i], 4);
+    }
+    for (int i = 0; i < F2_GSTAGES; ++i) {
+      tc::mbar_init(&g_full[i], 1);
+      tc::mbar_init(&g_empty[i], 8);
+    }
+    tc::mbar_init_fence();
+  }
+  if (warp == 8) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  // contiguous range of tiles for this CTA (tile = 512 samples of one utterance)
+  const int64_t tile_begin = a.ntiles * slot / per_blk;
+  const int64_t tile_end = a.ntiles * (slot + 1) / per_blk;
+  const int64_t my_tiles = tile_end - tile_begin;
+  bool ok = true;
+
+  if (warp < 8) {
+    // ------------- grad_y converters (staged fp32 rows -> bf16 hi/mid -> TMEM ring) --------------------------
+    // Two groups of four warps (one warp per TMEM lane quarter each) take alternate K-steps.  The rows come from
+    // the bulk-copy ring: the register pipeline of the first version only covered ~800 cycles of load latency
+    // (ncu r01t: converters stalled on first use, issuers idle on a_full); 4 stages x 32 KB of asynchronous
+    // copies are in flight per SM instead, and no register holds data that has not arrived yet.
+    const int grp = warp >> 2;
+    const int quarter = warp & 3;   // tcgen05.ld/st: a warp reaches TMEM lanes 32*(warp%4) .. +31 only
+    const int m = 32 * quarter + lane;  // TMEM lane = A row (c_local, h)
+    const int cl = m >> 1, h = m & 1;
+    const int c = c0 + cl;
+    const bool row_valid = c < C;
+    const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 halo = zero4;  // the 4 samples before the current stage (h = 1 rows start 4 samples early)
+    int64_t kc0 = 0;      // K-steps before the current tile (ring position of its first K-step)
+    int64_t gs = 0;       // staging stages consumed so far
+    auto emit = [&](const float4 (&v)[4], int64_t kc) {  // one K-step of this row -> TMEM ring slot
+      const int s = (int)(kc % F2_RING);
+      const uint32_t par = (uint32_t)((kc / F2_RING) & 1);
+      uint32_t hi[8], mid[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f2_split_bf16x2(v[j].x, v[j].y, hi[2 * j], mid[2 * j]);
+        f2_split_bf16x2(v[j].z, v[j].w, hi[2 * j + 1], mid[2 * j + 1]);
+      }
+      ok = ok && tc::mbar_wait(&a_empty[s], par ^ 1);
+      tc::fence_after_sync();
+      const uint32_t dst = tmem + lane_base + 2 * F2_DCOLS + 16 * s;
+      tc::tmem_st8(dst, hi);
+      tc::tmem_st8(dst + 8, mid);
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&a_full[s]);
+    };
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = tile_begin + it;
+      const int64_t b = tile / a.tiles_per_row;
+      const int64_t ti = tile - b * a.tiles_per_row;
+      const int64_t tb = ti * F2_TILE;
+      const int64_t left = T - tb;
+      const int span = (int)(left < F2_TILE ? left : F2_TILE);
+      const int nq = f2_ksteps(left, ti + 1 == a.tiles_per_row);
+      const int nstg = (span + F2_GSAMP - 1) / F2_GSAMP;
+      if (ti == 0) {
+        halo = zero4;  // utterance start: t < 0
+      } else if (it == 0) {  // this CTA starts in the middle of an utterance: fetch the 4 samples before its first tile
+        halo = (h && row_valid) ? __ldg(reinterpret_cast<const float4*>(a.g + (b * C + c) * T + tb - 4)) : zero4;
+      }
+      for (int st = 0; st < nstg; ++st) {
+        const int gb = (int)(gs & (F2_GSTAGES - 1));
+        ok = ok && tc::mbar_wait(&g_full[gb], (uint32_t)((gs / F2_GSTAGES) & 1));
+        const uint8_t* rowp = gst + gb * F2_GSTAGE_BYTES + cl * F2_GPITCH;
+        const int64_t ts = tb + (int64_t)F2_GSAMP * st;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = grp + 2 * u;  // K-step of the stage; K-step q of the tile belongs to group q & 1
+          const int q = 8 * st + j;
+          if (q < nq) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int off = 16 * j - 4 * h + 4 * i;  // sample offset within the stage (-4 only for j = 0, h = 1)
+              const int64_t tj = ts + off;
+              float4 w;
+              if (j == 0 && i == 0)
+                w = h ? halo : *reinterpret_cast<const float4*>(rowp);
+              else
+                w = *reinterpret_cast<const float4*>(rowp + 4 * off);
+              v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
+            }
+            emit(v, kc0 + q);
+          }
+        }
+        if (h) {  // carry the last 4 samples of the row into the next stage
+          const float4 w = *reinterpret_cast<const float4*>(rowp + 4 * (F2_GSAMP - 4));
+          halo = (row_valid && ts + F2_GSAMP - 4 < T) ? w : zero4;
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&g_empty[gb]);
+        ++gs;
+      }
+      if (nq > 8 * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
+        float4 v[4] = {h ? halo : zero4, zero4, zero4, zero4};
+        emit(v, kc0 + 8 * nstg);
+      }
+      kc0 += nq;
+    }
+  } else if (warp < 10) {
+    // ------------- MMA issuers: warp 8 owns the shifts rho = 0,1, warp 9 rho = 2,3 -------------------------------
+    // All lanes run the loop (warp-uniform control flow and operands); only the elected lane issues.
+    {
+      const int w = tc::uniform(warp - 8);
+      const int ntl = tc::uniform((int)my_tiles);
+      const int tpr = tc::uniform((int)a.tiles_per_row);
+      const int tile0 = tc::uniform((int)(tile_begin % a.tiles_per_row));
+      const uint32_t idesc = tc::make_idesc_f16(128, F2_N, tc::kFmtBF16, tc::kFmtBF16);
+      const uint64_t bdesc = tc::make_smem_desc(16, 128);  // in-place Toeplitz view, row pitch 8 samples
+      const uint32_t xs0 = tc::uniform((int)tc::smem_addr(xs));
+      const uint32_t tm = tc::uniform((int)tmem);
+      int kc = 0;          // K-steps issued so far (ring position)
+      int ti = tile0;      // tile index within its utterance
+      uint32_t acc = 0;    // 0: the next K-step overwrites the accumulators
+      for (int it = 0; it < ntl; ++it) {
+        const int64_t left = T - (int64_t)ti * F2_TILE;
+        const int nq = f2_ksteps(left, ti + 1 == tpr);
+        if (++ti == tpr) ti = 0;
+        const int xb = it & 1;
+        const int win = it / F2_FLUSH;
+        const int dbuf = win & 1;
+        ok = ok && tc::mbar_wait(&x_full[xb], (uint32_t)((it >> 1) & 1));
+        if (it % F2_FLUSH == 0) {
+          // this accumulator set was handed to the flush warps two windows ago: wait until it has been read out
+          ok = ok && tc::mbar_wait(&d_empty[dbuf], (uint32_t)(((win >> 1) & 1) ^ 1));
+          acc = 0;
+        }
+        const uint32_t d0 = tm + F2_DCOLS * dbuf + F2_N * (2 * w);
+        uint32_t b0 = xs0 + xb * (8 * F2_XLEN * 2) + (2 * (2 * w)) * F2_XLEN * 2;  // rho = 2w: hi copy, mid copy follows
+        for (int q = 0; q < nq; ++q) {
+          const int s = kc & (F2_RING - 1);
+          ok = ok && tc::mbar_wait(&a_full[s], (uint32_t)((kc / F2_RING) & 1));
+          tc::fence_after_sync();
+          const uint32_t ah = tm + 2 * F2_DCOLS + 16 * s, am = ah + 8;
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const uint64_t bh = tc::desc_at(bdesc, b0 + r * (2 * F2_XLEN * 2));
+              const uint64_t bm = tc::desc_at(bdesc, b0 + r * (2 * F2_XLEN * 2) + F2_XLEN * 2);
+              const uint32_t d = d0 + F2_N * r;
+              tc::mma_f16_ts(d, ah, bh, idesc, acc);
+              tc::mma_f16_ts(d, ah, bm, idesc, 1);
+              tc::mma_f16_ts(d, am, bh, idesc, 1);
+            }
+            tc::mma_commit(&a_empty[s]);
+          }
+          __syncwarp();
+          acc = 1;
+          b0 += 32;  // 16 samples
+          ++kc;
+        }
+        if (tc::elect_one()) {
+          tc::mma_commit(&x_empty[xb]);
+          if ((it + 1) % F2_FLUSH == 0 || it + 1 == ntl) tc::mma_commit(&d_full[dbuf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 10) {
+    // ------------- waveform producer: four shifted bf16 hi/mid copies of the tile ---------------------------
+    // xs_rho[i] = x[tb - H + i + rho].  Lane handles element pairs: even shifts store the pair (i, i+1) at word
+    // (i - rho)/2, odd shifts the pair (i+1, i+2) -- every store is one aligned 32-bit word.
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = tile_begin + it;
+      const int64_t b = tile / a.tiles_per_row;
+      const int64_t tb = (tile - b * a.tiles_per_row) * F2_TILE;
+      const int xb = (int)(it & 1);
+      const float* xr = a.x + b * a.xsb;
+      constexpr int NP = (F2_XLEN / 2 + 2 + 31) / 32;  // pair slots per lane (covers indices up to F2_XLEN + 3)
+      float v0[NP], v1[NP], v2[NP];
+#pragma unroll
+      for (int r = 0; r < NP; ++r) {
+        const int i = 2 * (lane + 32 * r);
+        const int64_t t = tb - H + i;
+        v0[r] = (t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
+        v1[r] = (t + 1 >= 0 && t + 1 < T) ? __ldg(xr + t + 1) : 0.f;
+        v2[r] = (t + 2 >= 0 && t + 2 < T) ? __ldg(xr + t + 2) : 0.f;
+      }
+      ok = ok && tc::mbar_wait(&x_empty[xb], (uint32_t)(((it >> 1) & 1) ^ 1));
+      uint32_t* base = reinterpret_cast<uint32_t*>(xs + (size_t)xb * 8 * F2_XLEN);
+#pragma unroll
+      for (int r = 0; r < NP; ++r) {
+        const int i = 2 * (lane + 32 * r);
+        uint32_t he, me, ho, mo;
+        f2_split_bf16x2(v0[r], v1[r], he, me);  // pair (i, i+1)
+        f2_split_bf16x2(v1[r], v2[r], ho, mo);  // pair (i+1, i+2)
+#pragma unroll
+        for (int rho = 0; rho < 4; ++rho) {
+          // even rho: word index (i - rho)/2 holds (i, i+1);  odd rho: word (i + 1 - rho)/2 holds (i+1, i+2)
+          const int wi = (rho & 1) ? (i + 1 - rho) / 2 : (i - rho) / 2;
+          const bool okw = ((rho & 1) ? (i + 1 - rho) : (i - rho)) >= 0 && wi < F2_XLEN / 2;
+          if (okw) {
+            base[(2 * rho) * (F2_XLEN / 2) + wi] = (rho & 1) ? ho : he;
+            base[(2 * rho + 1) * (F2_XLEN / 2) + wi] = (rho & 1) ? mo : me;
+          }
+        }
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&x_full[xb]);
+    }
+  } else if (warp == 11) {
+    // ------------- grad_y bulk-copy issuer: one 512-byte row copy per filter and stage (TMA engine, 1-D) --------
+    int64_t gs = 0;
+    const int nrows = (C - c0) < 64 ? (C - c0) : 64;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = tile_begin + it;
+      const int64_t b = tile / a.tiles_per_row;
+      const int64_t tb = (tile - b * a.tiles_per_row) * F2_TILE;
+      const int64_t left = T - tb;
+      const int span = (int)(left < F2_TILE ? left : F2_TILE);
+      const int nstg = (span + F2_GSAMP - 1) / F2_GSAMP;
+      for (int st = 0; st < nstg; ++st) {
+        const int gb = (int)(gs & (F2_GSTAGES - 1));
+        ok = ok && tc::mbar_wait(&g_empty[gb], (uint32_t)(((gs / F2_GSTAGES) & 1) ^ 1));
+        const int nsamp = span - F2_GSAMP * st < F2_GSAMP ? span - F2_GSAMP * st : F2_GSAMP;
+        const uint32_t bytes = (uint32_t)nsamp * 4;  // T % 4 == 0: a multiple of 16
+        if (lane == 0) tc::mbar_expect_tx(&g_full[gb], (uint32_t)nrows * bytes);
+        __syncwarp();
+        for (int r = lane; r < nrows; r += 32)
+          tc::bulk_load(gst + gb * F2_GSTAGE_BYTES + r * F2_GPITCH,
+                        a.g + (b * C + c0 + r) * T + tb + (int64_t)F2_GSAMP * st, bytes, &g_full[gb]);
+        ++gs;
+      }
+    }
+  } else if (warp >= 12) {
+    // ------------- flush warps: accumulator set -> the CTA's partial tile (fixed order, no atomics) ------------
+    const int quarter = warp & 3;
+    const int m = 32 * quarter + lane;
+    const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
+    float* myrow = a.partials + (((size_t)slot * a.nblk + fblk) * 128 + m) * F2_DCOLS;
+    const int64_t nwin = (my_tiles + F2_FLUSH - 1) / F2_FLUSH;
+    for (int64_t win = 0; win < nwin; ++win) {
+      const int dbuf = (int)(win & 1);
+      ok = ok && tc::mbar_wait(&d_full[dbuf], (uint32_t)((win >> 1) & 1));
+      tc::fence_after_sync();
+#pragma unroll 1
+      for (int ch = 0; ch < F2_DCOLS / 32; ++ch) {
+        uint32_t v[32];
+        tc::tmem_ld32(tmem + lane_base + F2_DCOLS * dbuf + 32 * ch, v);
+        tc::tmem_ld_wait();
+        float4* p = reinterpret_cast<float4*>(myrow + 32 * ch);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 o = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                 __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          if (win > 0) {
+            const float4 q = p[i];
+            o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
+          }
+          p[i] = o;
+        }
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&d_empty[dbuf]);
+    }
+    if (my_tiles == 0) {  // idle CTA: its partial tile must still read as zero
+      for (int i = 0; i < F2_DCOLS; i += 4) *reinterpret_cast<float4*>(myrow + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (!ok && lane == 0) *a.status = 1;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
+  (void)C;
+  return K <= 256 && T % 4 == 0 && g_dtype == SINC_DTYPE_F32 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
+         di.max_smem_optin >= F2_SM_TOTAL + 1024;
+}
+
+size_t tc16_bwd_filter_partial_bytes(int C) {
+  const int nblk = (C + 63) / 64;
+  return (size_t)kMaxPartialSlots * nblk * 128 * F2_DCOLS * sizeof(float);
+}
+
+cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy,
+                                   float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
+                                   cudaStream_t st) {
+  BwdFilterTc16Args a;
+  a.x = x;
+  a.xsb = x_stride_b;
+  a.g = reinterpret_cast<const float*>(gy);
+  a.B = B;
+  a.T = T;
+  a.C = bank.C;
+  a.K = bank.K;
+  a.partials = ws_partials;
+  a.nblk = (bank.C + 63) / 64;
+  a.tiles_per_row = ceil_div64(T, F2_TILE);
+  a.ntiles = B * a.tiles_per_row;
+  a.status = tc_status_device_ptr();
+  if (!a.status) return cudaErrorInvalidSymbol;
+  int64_t per_blk = di.sm_count / a.nblk;
+  if (per_blk < 1) per_blk = 1;
+  if (per_blk > a.ntiles) per_blk = a.ntiles;
+  if (per_blk > kMaxPartialSlots) per_blk = kMaxPartialSlots;
+  const int grid = (int)(per_blk * a.nblk);
+  const size_t smem = F2_SM_TOTAL + 1024;
+  cudaError_t e = cudaFuncSetAttribute(bwd_filter_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  bwd_filter_tc16_kernel<<<grid, F2_THREADS, smem, st>>>(a);
+  count_launch();
+  *slots_used = (int)per_blk;
+  return cudaGetLastError();
+}
+
+}  // namespace sinc
