@@ -163,11 +163,14 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   return t;
 }
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return true;
+  // fast path: no timer access while the barrier flips within a few thousand polls (the normal case)
+#pragma unroll 1
+  for (int spin = 0; spin < 4096; ++spin)
+    if (mbar_try_wait(bar, parity)) return true;
   const uint64_t t0 = global_timer_ns();
   for (;;) {
 #pragma unroll 1
-    for (int spin = 0; spin < 64; ++spin)
+    for (int spin = 0; spin < 256; ++spin)
       if (mbar_try_wait(bar, parity)) return true;
     if (global_timer_ns() - t0 > 1000000000ull) return false;
   }

@@ -245,34 +245,44 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
     for_each_run([&](int64_t b, int64_t s_out, int64_t e_out, int64_t c0, int nst, int64_t stage) {
       (void)b; (void)s_out; (void)e_out; (void)c0;
       // ------------- MMA issuers: warp 12 positions 0..63 of the stage, warp 13 positions 64..127 ----------------
-      if (lane == 0 && warp < 14) {
-        const int hf = warp - 12;
+      // All lanes of an issuer warp run the loop (warp-uniform operands stay in uniform registers); only the
+      // elected lane issues tcgen05 instructions.
+      if (warp < 14) {
+        const int hf = tc::uniform(warp - 12);
+        const int ncbu = tc::uniform(ncb);
+        const int nstu = tc::uniform(nst);
+        const int stg0 = tc::uniform((int)(stage & 0x3fffffff));  // only bits 0..1 of the stage counter matter below
+        const uint32_t tm = tc::uniform((int)tmem);
+        const uint32_t ring0 = tc::uniform((int)tc::smem_addr(ring));
         const uint32_t idesc = tc::make_idesc_f16(128, 64, tc::kFmtBF16, tc::kFmtBF16);
         const uint64_t bdesc = tc::make_smem_desc(H2_PLANE, 128);  // K chunk stride = plane, 8-row groups contiguous
-        for (int i = 0; i < nst; ++i) {
-          const int64_t sg = stage + i;
-          const int slot = (int)(sg & 3), buf = (int)(sg & 1);
+        for (int i = 0; i < nstu; ++i) {
+          const int sg = stg0 + i;
+          const int slot = sg & 3, buf = sg & 1;
           ok = ok && tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1));
           ok = ok && tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 2) & 1));
           tc::fence_after_sync();
-          const uint32_t d = tmem + 128 * buf + 64 * hf;
-          const uint32_t sbase = tc::smem_addr(ring + slot * H2_SLOT) + hf * 64 * 16;
-          uint32_t acc = 0;
-          for (int e = 0; e < 2; ++e) {
-            uint32_t ah = tmem + 256 + 32 * e;
-            uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
-            for (int cb = 0; cb < ncb; ++cb) {
-              const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
-              tc::mma_f16_ts(d, ah, dh, idesc, acc);
-              tc::mma_f16_ts(d, ah, dm, idesc, 1);
-              tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
-              acc = 1;
-              ah += 8;
-              bh += 2 * H2_PLANE;
+          const uint32_t d = tm + 128 * buf + 64 * hf;
+          const uint32_t sbase = ring0 + slot * H2_SLOT + hf * 64 * 16;
+          if (tc::elect_one()) {
+            uint32_t acc = 0;
+            for (int e = 0; e < 2; ++e) {
+              uint32_t ah = tm + 256 + 32 * e;
+              uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
+              for (int cb = 0; cb < ncbu; ++cb) {
+                const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
+                tc::mma_f16_ts(d, ah, dh, idesc, acc);
+                tc::mma_f16_ts(d, ah, dm, idesc, 1);
+                tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
+                acc = 1;
+                ah += 8;
+                bh += 2 * H2_PLANE;
+              }
             }
+            tc::mma_commit(&b_empty[slot]);
+            tc::mma_commit(&d_full[2 * buf + hf]);
           }
-          tc::mma_commit(&b_empty[slot]);
-          tc::mma_commit(&d_full[2 * buf + hf]);
+          __syncwarp();
         }
       }
       __syncwarp();
