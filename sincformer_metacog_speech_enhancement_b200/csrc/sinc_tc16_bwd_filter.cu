@@ -324,26 +324,48 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     }
   } else if (warp == 11) {
     // ------------- grad_y bulk-copy issuer: one 512-byte row copy per filter and stage (TMA engine, 1-D) --------
-    int64_t gs = 0;
-    const int nrows = (C - c0) < 64 ? (C - c0) : 64;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int64_t tile = tile_begin + it;
-      const int64_t b = tile / a.tiles_per_row;
-      const int64_t tb = (tile - b * a.tiles_per_row) * F2_TILE;
-      const int64_t left = T - tb;
-      const int span = (int)(left < F2_TILE ? left : F2_TILE);
-      const int nstg = (span + F2_GSAMP - 1) / F2_GSAMP;
-      for (int st = 0; st < nstg; ++st) {
-        const int gb = (int)(gs & (F2_GSTAGES - 1));
-        ok = ok && tc::mbar_wait(&g_empty[gb], (uint32_t)(((gs / F2_GSTAGES) & 1) ^ 1));
-        const int nsamp = span - F2_GSAMP * st < F2_GSAMP ? span - F2_GSAMP * st : F2_GSAMP;
-        const uint32_t bytes = (uint32_t)nsamp * 4;  // T % 4 == 0: a multiple of 16
-        if (lane == 0) tc::mbar_expect_tx(&g_full[gb], (uint32_t)nrows * bytes);
-        __syncwarp();
-        for (int r = lane; r < nrows; r += 32)
-          tc::bulk_load(gst + gb * F2_GSTAGE_BYTES + r * F2_GPITCH,
-                        a.g + (b * C + c0 + r) * T + tb + (int64_t)F2_GSAMP * st, bytes, &g_full[gb]);
-        ++gs;
+    // cp.async.bulk takes uniform operands: the loop over rows is warp-uniform and one elected lane issues (a
+    // per-lane loop costs an ELECT/R2UR round trip per copy -- ncu r01x: 3000 cycles per stage, converters starved).
+    {
+      const int ntl = tc::uniform((int)my_tiles);
+      const int tpr = tc::uniform((int)a.tiles_per_row);
+      int ti = tc::uniform((int)(tile_begin % a.tiles_per_row));
+      int64_t brow = tile_begin / a.tiles_per_row;  // utterance of the current tile (uniform: from blockIdx only)
+      const int nrows = (C - c0) < 64 ? (C - c0) : 64;
+      const uint32_t gst0 = tc::uniform((int)tc::smem_addr(gst));
+      int gs = 0;
+      for (int it = 0; it < ntl; ++it) {
+        const int64_t tb = (int64_t)ti * F2_TILE;
+        const int64_t left = T - tb;
+        const int span = (int)(left < F2_TILE ? left : F2_TILE);
+        const int nstg = (span + F2_GSAMP - 1) / F2_GSAMP;
+        const float* src_tile = a.g + (brow * C + c0) * T + tb;
+        for (int st = 0; st < nstg; ++st) {
+          const int gb = gs & (F2_GSTAGES - 1);
+          ok = ok && tc::mbar_wait(&g_empty[gb], (uint32_t)(((gs / F2_GSTAGES) & 1) ^ 1));
+          const int nsamp = span - F2_GSAMP * st < F2_GSAMP ? span - F2_GSAMP * st : F2_GSAMP;
+          const uint32_t bytes = (uint32_t)nsamp * 4;  // T % 4 == 0: a multiple of 16
+          if (tc::elect_one()) {
+            tc::mbar_expect_tx(&g_full[gb], (uint32_t)nrows * bytes);
+            const float* src = src_tile + F2_GSAMP * st;
+            uint32_t dst = gst0 + gb * F2_GSTAGE_BYTES;
+            const uint32_t bar = tc::smem_addr(&g_full[gb]);
+#pragma unroll 4
+            for (int r = 0; r < nrows; ++r) {
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                           "l"(src), "r"(bytes), "r"(bar)
+                           : "memory");
+              src += T;
+              dst += F2_GPITCH;
+            }
+          }
+          __syncwarp();
+          ++gs;
+        }
+        if (++ti == tpr) {
+          ti = 0;
+          ++brow;
+        }
       }
     }
   } else if (warp >= 12) {
