@@ -18,8 +18,8 @@
 // computes every tap in both interleaves: 78 % useful).  Each g sample is converted twice (once per interleave).
 //
 // A (= grad_y) is staged as raw fp32 rows by 1-D bulk copies (4 stages x 64 rows x 128 samples in flight), read back
-// row-per-lane, split into bf16 hi/mid and written with tcgen05.st into an 8-deep TMEM ring; every MMA is the TS
-// form (A from TMEM), the B tiles are 1 KB each.
+// row-per-lane, split into bf16 hi/mid and written with tcgen05.st into a TMEM ring of 4 slots x 2 K-steps (one
+// producer/issuer handshake per slot); every MMA is the TS form (A from TMEM), the B tiles are 1 KB each.
 //     TMEM  two accumulator sets [0,128) / [128,256): D_rho = 32 columns  |  A ring [256,384): 16 columns per K-step
 //     SMEM  grad_y staging ring 136 KB  |  2 x 4 x (hi,mid) shifted waveform tiles, 25 KB
 // The accumulators are double-buffered: while one set is flushed (read-modify-write of the CTA's own partial tile in
@@ -35,8 +35,10 @@ constexpr int F2_THREADS = 512;  // warps 0-7 grad_y converters (2 groups), 8-9 
                                  // 11 grad_y bulk-copy issuer, 12-15 flush
 constexpr int F2_N = 32;                    // MMA N (tap columns per shift rho)
 constexpr int F2_TILE = 512;                // samples per tile = 32 K-steps of 16 samples
-constexpr int F2_XLEN = 784;                // bf16 elements per shifted waveform copy: 8*31 + 16*33 + 8 rounded up
-constexpr int F2_RING = 8;                  // TMEM A ring depth (K-steps)
+constexpr int F2_XLEN = 800;                // bf16 elements per shifted waveform copy: 8*31 + 16*34 + 8
+constexpr int F2_KPS = 2;                   // K-steps per A ring slot (one producer/issuer handshake per slot)
+constexpr int F2_RING = 4;                  // TMEM A ring depth (slots of F2_KPS K-steps = 16*F2_KPS columns)
+static_assert(8 % F2_KPS == 0 && (F2_RING & (F2_RING - 1)) == 0 && F2_RING * F2_KPS * 16 <= 256, "A ring geometry");
 constexpr int F2_FLUSH = 8;                 // tiles per accumulation window (4096 samples)
 constexpr int F2_DCOLS = 4 * F2_N;          // 128
 constexpr int F2_GSAMP = 128;               // samples per grad_y staging stage (8 K-steps)
@@ -146,22 +148,31 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 halo = zero4;  // the 4 samples before the current stage (h = 1 rows start 4 samples early)
-    int64_t kc0 = 0;      // K-steps before the current tile (ring position of its first K-step)
+    int64_t cc0 = 0;      // ring slots (chunks of F2_KPS K-steps) before the current tile
     int64_t gs = 0;       // staging stages consumed so far
-    auto emit = [&](const float4 (&v)[4], int64_t kc) {  // one K-step of this row -> TMEM ring slot
-      const int s = (int)(kc % F2_RING);
-      const uint32_t par = (uint32_t)((kc / F2_RING) & 1);
-      uint32_t hi[8], mid[8];
+    auto emit = [&](const float4 (&v)[4 * F2_KPS], int64_t cc) {  // F2_KPS K-steps of this row -> one TMEM ring slot
+      const int s = (int)(cc & (F2_RING - 1));
+      const uint32_t par = (uint32_t)((cc / F2_RING) & 1);
+      uint32_t hi[8 * F2_KPS], mid[8 * F2_KPS];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 4 * F2_KPS; ++j) {
         f2_split_bf16x2(v[j].x, v[j].y, hi[2 * j], mid[2 * j]);
         f2_split_bf16x2(v[j].z, v[j].w, hi[2 * j + 1], mid[2 * j + 1]);
       }
       ok = ok && tc::mbar_wait(&a_empty[s], par ^ 1);
       tc::fence_after_sync();
-      const uint32_t dst = tmem + lane_base + 2 * F2_DCOLS + 16 * s;
-      tc::tmem_st8(dst, hi);
-      tc::tmem_st8(dst + 8, mid);
+      const uint32_t dst = tmem + lane_base + 2 * F2_DCOLS + 16 * F2_KPS * s;
+#pragma unroll
+      for (int kk = 0; kk < F2_KPS; ++kk) {  // per K-step: 8 columns hi, 8 columns mid
+        uint32_t th[8], tm8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          th[e] = hi[8 * kk + e];
+          tm8[e] = mid[8 * kk + e];
+        }
+        tc::tmem_st8(dst + 16 * kk, th);
+        tc::tmem_st8(dst + 16 * kk + 8, tm8);
+      }
       tc::tmem_st_wait();
       tc::fence_before_sync();
       __syncwarp();
@@ -187,23 +198,23 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         const uint8_t* rowp = gst + gb * F2_GSTAGE_BYTES + cl * F2_GPITCH;
         const int64_t ts = tb + (int64_t)F2_GSAMP * st;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = grp + 2 * u;  // K-step of the stage; K-step q of the tile belongs to group q & 1
-          const int q = 8 * st + j;
-          if (q < nq) {
-            float4 v[4];
+        for (int u = 0; u < 8 / F2_KPS / 2; ++u) {
+          const int pch = grp + 2 * u;                 // chunk of the stage; chunk ch of the tile belongs to group ch & 1
+          const int ch = (8 / F2_KPS) * st + pch;
+          if (F2_KPS * ch < nq) {
+            float4 v[4 * F2_KPS];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int off = 16 * j - 4 * h + 4 * i;  // sample offset within the stage (-4 only for j = 0, h = 1)
+            for (int i = 0; i < 4 * F2_KPS; ++i) {
+              const int off = 16 * F2_KPS * pch - 4 * h + 4 * i;  // sample offset within the stage (-4 only for pch = 0, h = 1)
               const int64_t tj = ts + off;
               float4 w;
-              if (j == 0 && i == 0)
+              if (pch == 0 && i == 0)
                 w = h ? halo : *reinterpret_cast<const float4*>(rowp);
               else
                 w = *reinterpret_cast<const float4*>(rowp + 4 * off);
               v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
             }
-            emit(v, kc0 + q);
+            emit(v, cc0 + ch);
           }
         }
         if (h) {  // carry the last 4 samples of the row into the next stage
@@ -215,10 +226,13 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         ++gs;
       }
       if (nq > 8 * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
-        float4 v[4] = {h ? halo : zero4, zero4, zero4, zero4};
-        emit(v, kc0 + 8 * nstg);
+        float4 v[4 * F2_KPS];
+#pragma unroll
+        for (int i = 0; i < 4 * F2_KPS; ++i) v[i] = zero4;
+        if (h) v[0] = halo;
+        emit(v, cc0 + (8 / F2_KPS) * nstg);
       }
-      kc0 += nq;
+      cc0 += (nq + F2_KPS - 1) / F2_KPS;
     }
   } else if (warp < 10) {
     // ------------- MMA issuers: warp 8 owns the shifts rho = 0,1, warp 9 rho = 2,3 -------------------------------
@@ -232,7 +246,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
       const uint64_t bdesc = tc::make_smem_desc(16, 128);  // in-place Toeplitz view, row pitch 8 samples
       const uint32_t xs0 = tc::uniform((int)tc::smem_addr(xs));
       const uint32_t tm = tc::uniform((int)tmem);
-      int kc = 0;          // K-steps issued so far (ring position)
+      int cc = 0;          // ring slots consumed so far
       int ti = tile0;      // tile index within its utterance
       uint32_t acc = 0;    // 0: the next K-step overwrites the accumulators
       for (int it = 0; it < ntl; ++it) {
@@ -250,27 +264,31 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         }
         const uint32_t d0 = tm + F2_DCOLS * dbuf + F2_N * (2 * w);
         uint32_t b0 = xs0 + xb * (8 * F2_XLEN * 2) + (2 * (2 * w)) * F2_XLEN * 2;  // rho = 2w: hi copy, mid copy follows
-        for (int q = 0; q < nq; ++q) {
-          const int s = kc & (F2_RING - 1);
-          ok = ok && tc::mbar_wait(&a_full[s], (uint32_t)((kc / F2_RING) & 1));
+        const int nch = (nq + F2_KPS - 1) / F2_KPS;  // K-steps past nq carry zeros in A: harmless
+        for (int ch = 0; ch < nch; ++ch) {
+          const int s = cc & (F2_RING - 1);
+          ok = ok && tc::mbar_wait(&a_full[s], (uint32_t)((cc / F2_RING) & 1));
           tc::fence_after_sync();
-          const uint32_t ah = tm + 2 * F2_DCOLS + 16 * s, am = ah + 8;
           if (tc::elect_one()) {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const uint64_t bh = tc::desc_at(bdesc, b0 + r * (2 * F2_XLEN * 2));
-              const uint64_t bm = tc::desc_at(bdesc, b0 + r * (2 * F2_XLEN * 2) + F2_XLEN * 2);
-              const uint32_t d = d0 + F2_N * r;
-              tc::mma_f16_ts(d, ah, bh, idesc, acc);
-              tc::mma_f16_ts(d, ah, bm, idesc, 1);
-              tc::mma_f16_ts(d, am, bh, idesc, 1);
+            for (int kk = 0; kk < F2_KPS; ++kk) {
+              const uint32_t ah = tm + 2 * F2_DCOLS + 16 * F2_KPS * s + 16 * kk, am = ah + 8;
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const uint64_t bh = tc::desc_at(bdesc, b0 + 32 * kk + r * (2 * F2_XLEN * 2));
+                const uint64_t bm = tc::desc_at(bdesc, b0 + 32 * kk + r * (2 * F2_XLEN * 2) + F2_XLEN * 2);
+                const uint32_t d = d0 + F2_N * r;
+                tc::mma_f16_ts(d, ah, bh, idesc, kk == 0 ? acc : 1u);
+                tc::mma_f16_ts(d, ah, bm, idesc, 1);
+                tc::mma_f16_ts(d, am, bh, idesc, 1);
+              }
             }
             tc::mma_commit(&a_empty[s]);
           }
           __syncwarp();
           acc = 1;
-          b0 += 32;  // 16 samples
-          ++kc;
+          b0 += 32 * F2_KPS;  // 16 samples per K-step
+          ++cc;
         }
         if (tc::elect_one()) {
           tc::mma_commit(&x_empty[xb]);
