@@ -35,8 +35,8 @@ constexpr int F2_THREADS = 512;  // warps 0-7 grad_y converters (2 groups), 8-9 
                                  // 11 grad_y bulk-copy issuer, 12-15 flush
 constexpr int F2_N = 32;                    // MMA N (tap columns per shift rho)
 constexpr int F2_TILE = 512;                // samples per tile = 32 K-steps of 16 samples
-constexpr int F2_XLEN = 800;                // bf16 elements per shifted waveform copy: 8*31 + 16*34 + 8
-constexpr int F2_KPS = 2;                   // K-steps per A ring slot (one producer/issuer handshake per slot)
+constexpr int F2_XLEN = 832;                // bf16 elements per shifted waveform copy: >= 8*31 + 16*36
+constexpr int F2_KPS = 4;                   // K-steps per A ring slot (one producer/issuer handshake per slot)
 constexpr int F2_RING = 4;                  // TMEM A ring depth (slots of F2_KPS K-steps = 16*F2_KPS columns)
 static_assert(8 % F2_KPS == 0 && (F2_RING & (F2_RING - 1)) == 0 && F2_RING * F2_KPS * 16 <= 256, "A ring geometry");
 constexpr int F2_FLUSH = 8;                 // tiles per accumulation window (4096 samples)
@@ -273,15 +273,18 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
 #pragma unroll
             for (int kk = 0; kk < F2_KPS; ++kk) {
               const uint32_t ah = tm + 2 * F2_DCOLS + 16 * F2_KPS * s + 16 * kk, am = ah + 8;
-#pragma unroll
-              for (int r = 0; r < 2; ++r) {
-                const uint64_t bh = tc::desc_at(bdesc, b0 + 32 * kk + r * (2 * F2_XLEN * 2));
-                const uint64_t bm = tc::desc_at(bdesc, b0 + 32 * kk + r * (2 * F2_XLEN * 2) + F2_XLEN * 2);
-                const uint32_t d = d0 + F2_N * r;
-                tc::mma_f16_ts(d, ah, bh, idesc, kk == 0 ? acc : 1u);
-                tc::mma_f16_ts(d, ah, bm, idesc, 1);
-                tc::mma_f16_ts(d, am, bh, idesc, 1);
-              }
+              // consecutive MMAs into the same accumulator serialise on its TMEM read-modify-write: alternate the
+              // two shifts this issuer owns so that dependent instructions are never adjacent
+              const uint64_t bh0 = tc::desc_at(bdesc, b0 + 32 * kk), bm0 = tc::desc_at(bdesc, b0 + 32 * kk + F2_XLEN * 2);
+              const uint64_t bh1 = tc::desc_at(bdesc, b0 + 32 * kk + 2 * F2_XLEN * 2);
+              const uint64_t bm1 = tc::desc_at(bdesc, b0 + 32 * kk + 3 * F2_XLEN * 2);
+              const uint32_t acc0 = kk == 0 ? acc : 1u;
+              tc::mma_f16_ts(d0, ah, bh0, idesc, acc0);
+              tc::mma_f16_ts(d0 + F2_N, ah, bh1, idesc, acc0);
+              tc::mma_f16_ts(d0, ah, bm0, idesc, 1);
+              tc::mma_f16_ts(d0 + F2_N, ah, bm1, idesc, 1);
+              tc::mma_f16_ts(d0, am, bh0, idesc, 1);
+              tc::mma_f16_ts(d0 + F2_N, am, bh1, idesc, 1);
             }
             tc::mma_commit(&a_empty[s]);
           }
