@@ -141,19 +141,24 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   const Bank bank = to_bank(fb);
   const int engine = g_engine.load();
   const bool tc_ok = tc_fwd_supported(bank.C, bank.K, T, y, y_dtype, di);
-  if (engine == SINC_ENGINE_TC && !tc_ok) return SINC_E_ENGINE;
+  const bool tc16_ok = tc16_fwd_supported(bank.C, bank.K, T, y, y_dtype, di);
+  if (engine == SINC_ENGINE_TC && !tc_ok && !tc16_ok) return SINC_E_ENGINE;
   if (engine == SINC_ENGINE_TC_TF32 && !tc_ok) return SINC_E_ENGINE;
-  const bool use_tc = tc_ok && (engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
-                                (engine == SINC_ENGINE_AUTO && kAutoPrefersTcForward));
+  const bool want_tc = engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
+                       (engine == SINC_ENGINE_AUTO && kAutoPrefersTcForward);
+  const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
+  const bool use_tc = want_tc && tc_ok && !use_tc16;
   cudaError_t e;
-  if (use_tc) {
+  if (use_tc16) {
+    e = launch_fwd_tc16(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
+  } else if (use_tc) {
     e = launch_fwd_tc(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
   } else {
     if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
     e = launch_fwd_fma(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return (int)e;
-  t_last_mask.store((t_last_mask.load() & ~1) | (use_tc ? 1 : 0));
+  t_last_mask.store((t_last_mask.load() & ~9) | ((use_tc || use_tc16) ? 1 : 0) | (use_tc16 ? 8 : 0));
   return 0;
 }
 
@@ -218,7 +223,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     mask |= (use_tc || use_tc16) ? 4 : 0;
     mask |= use_tc16 ? 32 : 0;
   }
-  t_last_mask.store((t_last_mask.load() & 1) | mask);
+  t_last_mask.store((t_last_mask.load() & 9) | mask);
   return 0;
 }
 

@@ -22,8 +22,9 @@
 // producer/issuer handshake per slot); every MMA is the TS form (A from TMEM), the B tiles are 1 KB each.
 //     TMEM  two accumulator sets [0,128) / [128,256): D_rho = 32 columns  |  A ring [256,384): 16 columns per K-step
 //     SMEM  grad_y staging ring 136 KB  |  2 x 4 x (hi,mid) shifted waveform tiles, 25 KB
-// The accumulators are double-buffered: while one set is flushed (read-modify-write of the CTA's own partial tile in
-// the workspace, every F2_FLUSH tiles) the MMAs of the next window run into the other.
+// The accumulators are flushed every F2_FLUSH tiles (read-modify-write of the CTA's own partial tile in the
+// workspace), which bounds the length of any fp32 accumulation chain; see the issuer for why the flush does not
+// overlap the next window's MMAs.
 #include <cuda_bf16.h>
 
 #include "sinc_internal.h"
@@ -49,7 +50,8 @@ constexpr int F2_GSTAGE_BYTES = 64 * F2_GPITCH;
 constexpr int F2_SM_G = 0;                  // [F2_GSTAGES][64 rows][F2_GPITCH]
 constexpr int F2_SM_X = F2_SM_G + F2_GSTAGES * F2_GSTAGE_BYTES;  // [buf 2][rho 4][hi/mid 2][F2_XLEN] bf16
 constexpr int F2_SM_BAR = F2_SM_X + 2 * 8 * F2_XLEN * 2;
-constexpr int F2_SM_TOTAL = F2_SM_BAR + 256;
+constexpr int F2_SM_TOTAL = F2_SM_BAR + 512;
+static_assert(28 + F2_GSTAGES <= 32, "barrier table: tmem_slot lives at bars + 32");
 static_assert((F2_XLEN * 2) % 16 == 0, "waveform copies must stay 16-byte aligned");
 
 struct BwdFilterTc16Args {
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   uint64_t* d_empty = bars + 22;      // [2]  flush warps (4) -> issuers
   uint64_t* g_full = bars + 24;       // [F2_GSTAGES]  bulk copies (expect_tx) -> converters
   uint64_t* g_empty = bars + 28;      // [F2_GSTAGES]  converters (8 warps) -> copy issuer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);  // after g_empty[F2_GSTAGES]
   uint8_t* gst = smem + F2_SM_G;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,6 +262,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         if (it % F2_FLUSH == 0) {
           // this accumulator set was handed to the flush warps two windows ago: wait until it has been read out
           ok = ok && tc::mbar_wait(&d_empty[dbuf], (uint32_t)(((win >> 1) & 1) ^ 1));
+          // ... and until the PREVIOUS window's set has been read out as well.  Letting the flush of one set overlap
+          // the MMAs into the other produced rare, run-to-run varying errors in rows of the last lane quarter
+          // (tools/gf_debug.py, r02k: 3e-3 on a few filters with > 8 tiles per CTA; never without the overlap).
+          // The root cause is not understood yet, so the issuer stalls for the ~3 us a flush takes (once per
+          // F2_FLUSH tiles, ~3 % of the kernel) -- the two sets still let the flush overlap the converters.
+          if (win >= 1) ok = ok && tc::mbar_wait(&d_empty[dbuf ^ 1], (uint32_t)(((win - 1) >> 1) & 1));
           acc = 0;
         }
         const uint32_t d0 = tm + F2_DCOLS * dbuf + F2_N * (2 * w);

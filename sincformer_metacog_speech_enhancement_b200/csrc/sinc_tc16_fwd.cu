@@ -1,0 +1,332 @@
+// tcgen05 engine, forward, 16-bit split operands:  y[b,c,t] = sum_k w[c,k] x[b,t+k-H]   (perception.py:117-118)
+// on kind::f16 tensor cores with fp32-grade accuracy: scaled fp16 hi/lo split, sm_100a only.
+//
+// Precision.  fp16 has the 11-bit significand of TF32 at twice the tensor-core rate; its 5-bit exponent is handled
+// by exact power-of-two scaling.  Per waveform tile sx = 2^e puts max|x| in [2^13, 2^14); per filter sw_c does the
+// same for max_k|w[c,k]|.  Then  x*sx = x_hi + x_lo,  w*sw = w_hi + w_lo  (each rounded to fp16, 22 bits together;
+// elements more than 2^-17 below their tile/filter maximum lose relative -- not max-norm -- precision) and
+//     y = (W_hi X_hi + W_hi X_lo + W_lo X_hi) / (sx * sw_c)          fp32 accumulation in TMEM,
+// the dropped W_lo X_lo term is 2^-22 relative.  Against the fp64 oracle: ~1e-7 max-norm relative (gate 1e-5).
+//
+// Formulation.  With t = t0 + 8j + r (r = phase 0..7):
+//     Y[(c,r), j] = sum_s  W'[(c,r), s] * X[j, s],     W'[(c,r), s] = w[c, s - r],   X[j, s] = xt[8j + s]
+// where xt[i] = x[b, t0 - H + i] is the waveform tile.  X is a Toeplitz matrix with a row pitch of 8 fp16 samples
+// = 16 bytes = the row pitch of a no-swizzle K-major core matrix, so the UMMA descriptor (LBO = 16, SBO = 128)
+// reads it IN PLACE from the 2.3 KB tile; a K-step of 16 taps is a +32-byte start address.  M = 8 phases x 16
+// filters = 128 rows per CTA, N = 112 (896 output samples), K = 272 >= K_taps + 7.
+//
+// On-chip budget per CTA (one CTA per SM, 16 filters; CTAs alternate between the filter blocks):
+//     TMEM  D0 [0,112)  D1 [128,240)  W'_hi [240,376)  W'_lo [376,512)   (16-bit operands: two taps per column)
+//     SMEM  2 x (x_hi, x_lo) tiles 9 KB | 2 x output staging 57 KB (double-buffered against the bulk stores)
+// Every MMA takes A from TMEM; shared memory only serves the 3.5 KB B operand (64 B/clk).
+//
+// Warp roles (224 threads): warps 0-3 epilogue (TMEM -> scale -> phase-interleaved staging -> 1-D bulk stores
+// of 3.5 KB rows), warps 4 and 6 MMA issuers (even / odd tiles, warp-uniform issue loops), warp 5 waveform
+// producer (global -> max -> scale -> fp16 hi/lo -> smem).
+#include <cuda_fp16.h>
+
+#include "sinc_internal.h"
+#include "sinc_synth.cuh"
+#include "sinc_tc.cuh"
+
+namespace sinc {
+
+constexpr int U_THREADS = 224;
+constexpr int U_FB = 16;                  // filters per CTA
+constexpr int U_NJ = 112;                 // MMA N: output groups of 8 samples per tile
+constexpr int U_TT = 8 * U_NJ;            // 896 output samples per tile
+constexpr int U_KS = 272;                 // GEMM K (taps + phase shift, zero padded): 17 K-steps
+constexpr int U_XT = U_TT + U_KS;         // 1168 waveform samples per tile
+constexpr int U_PITCH = U_TT + 8;         // floats; +8 makes the phase-interleaved staging writes conflict free
+constexpr int U_WPITCH = 272;             // floats, setup scratch (one filter per row)
+constexpr int U_TM_D1 = 128, U_TM_WHI = 240, U_TM_WLO = 376;
+
+constexpr int U_SM_X = 0;                                     // [buf 2][hi/lo 2][U_XT] fp16
+constexpr int U_SM_STAGE = U_SM_X + ((2 * 2 * U_XT * 2 + 127) / 128) * 128;
+constexpr int U_SM_SCALE = U_SM_STAGE + 2 * U_FB * U_PITCH * 4;   // x inverse scales [4], filter inverse scales [16]
+constexpr int U_SM_BAR = U_SM_SCALE + 128;
+constexpr int U_SM_TOTAL = U_SM_BAR + 128;
+static_assert(U_FB * U_WPITCH * 4 <= U_FB * U_PITCH * 4, "setup scratch must fit in one staging buffer");
+
+struct FwdTc16Args {
+  Bank bank;
+  const float* x;
+  int64_t xsb;
+  float* y;
+  int64_t B, T;
+  int nblk;            // filter blocks of 16
+  int ksteps;          // ceil((K + 7) / 16) <= 17
+  int64_t tiles_per_row;
+  int64_t ntiles;      // B * tiles_per_row (per filter block)
+  int* status;
+};
+
+// power-of-two scale that puts `m` (>= 0) into [2^13, 2^14): returns the exponent, clamped so that both the
+// scale and its inverse are normal floats; m = 0 or non-finite -> 0
+__device__ __forceinline__ int u_scale_exp(float m) {
+  const uint32_t bits = __float_as_uint(m);
+  const int e = (int)((bits >> 23) & 0xffu) - 127;
+  if (m == 0.f || e == 128) return 0;
+  int se = 13 - e;
+  se = se > 100 ? 100 : se;
+  se = se < -100 ? -100 : se;
+  return se;
+}
+__device__ __forceinline__ float u_pow2(int e) { return __uint_as_float((uint32_t)(127 + e) << 23); }
+
+// v (already scaled) -> fp16 hi (RN) and fp16 lo = RN(v - hi), as raw 16-bit patterns
+__device__ __forceinline__ void u_split_f16(float v, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(v);
+  const __half l = __float2half_rn(v - __half2float(h));
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(l);
+}
+
+__global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint16_t* xbuf = reinterpret_cast<uint16_t*>(smem + U_SM_X);  // [buf][hi/lo][U_XT]
+  float* stage = reinterpret_cast<float*>(smem + U_SM_STAGE);   // [2][U_FB][U_PITCH]
+  float* xinv = reinterpret_cast<float*>(smem + U_SM_SCALE);    // [4]  1 / sx of tile it & 3
+  float* winv = xinv + 4;                                       // [16] 1 / sw_c
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + U_SM_BAR);
+  uint64_t* x_full = bars + 0;     // [2]
+  uint64_t* x_empty = bars + 2;    // [2]
+  uint64_t* acc_full = bars + 4;   // [2]
+  uint64_t* acc_empty = bars + 6;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int C = a.bank.C, K = a.bank.K, H = (K - 1) / 2;
+  const int per_blk = gridDim.x / a.nblk;
+  const int fblk = blockIdx.x % a.nblk;
+  const int slot = blockIdx.x / a.nblk;
+  const int c0 = fblk * U_FB;
+  const int64_t T = a.T;
+
+  // ---------------- setup: barriers, TMEM, filters --------------------------------------------------
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&x_full[i], 1);
+      tc::mbar_init(&x_empty[i], 1);
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::mbar_init_fence();
+  }
+  if (warp == 4) {
+    tc::tmem_alloc(tmem_slot, 512);
+    tc::tmem_relinquish();
+  }
+  float* wsc = stage;  // fp32 filters [16][U_WPITCH], zero outside [0, K)
+  for (int i = tid; i < U_FB * U_WPITCH; i += U_THREADS) wsc[i] = 0.f;
+  __syncthreads();
+  for (int cl = warp; cl < U_FB; cl += U_THREADS / 32) {  // 7 warps share the 16 filters
+    const int c = c0 + cl;
+    float mx = 0.f;
+    if (c < C)
+      synth_filter_warp(a.bank, c, lane, [&](int k, double w) {
+        const float wf = (float)w;
+        wsc[cl * U_WPITCH + k] = wf;
+        mx = fmaxf(mx, fabsf(wf));
+      });
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int se = u_scale_exp(mx);
+    if (lane == 0) winv[cl] = u_pow2(-se);
+    const float sw = u_pow2(se);
+    __syncwarp();
+    for (int k = lane; k < K; k += 32) wsc[cl * U_WPITCH + k] *= sw;  // exact (power of two)
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  // W' -> TMEM: lane = row m = 8*cl + r, column = tap pair (s, s+1), W'[m, s] = w[cl, s - r]
+  if (warp < 4) {
+    const int m = tid, cl = m >> 3, r = m & 7;
+    const uint32_t base = tmem + ((uint32_t)(32 * warp) << 16);
+    const float* wr = wsc + cl * U_WPITCH;
+    for (int s0 = 0; s0 < U_KS; s0 += 16) {
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k0 = s0 + 2 * e - r, k1 = k0 + 1;
+        uint16_t h0, l0, h1, l1;
+        u_split_f16((k0 >= 0 && k0 < K) ? wr[k0] : 0.f, h0, l0);
+        u_split_f16((k1 >= 0 && k1 < K) ? wr[k1] : 0.f, h1, l1);
+        hi[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        lo[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      }
+      tc::tmem_st8(base + U_TM_WHI + s0 / 2, hi);
+      tc::tmem_st8(base + U_TM_WLO + s0 / 2, lo);
+    }
+    tc::tmem_st_wait();
+  }
+  tc::fence_before_sync();
+  __syncthreads();  // the setup scratch becomes staging buffer 0
+  tc::fence_after_sync();
+
+  const int64_t my_tiles = slot < a.ntiles ? (a.ntiles - slot + per_blk - 1) / per_blk : 0;
+  bool ok = true;
+
+  if (warp == 5) {
+    // ---------------- producer: waveform tile -> max -> scale -> fp16 hi / lo in shared memory ---------------
+    constexpr int NV = (U_XT + 31) / 32;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      const int64_t tile = slot + it * per_blk;
+      const int64_t b = tile / a.tiles_per_row;
+      const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
+      const float* xr = a.x + b * a.xsb;
+      float v[NV];
+      float mx = 0.f;
+#pragma unroll
+      for (int r = 0; r < NV; ++r) {
+        const int i = lane + 32 * r;
+        const int64_t t = t0 - H + i;
+        v[r] = (i < U_XT && t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
+        mx = fmaxf(mx, fabsf(v[r]));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int se = u_scale_exp(mx);
+      const float sx = u_pow2(se);
+      ok = ok && tc::mbar_wait(&x_empty[buf], par ^ 1);
+      if (lane == 0) xinv[it & 3] = u_pow2(-se);
+      uint16_t* xh = xbuf + (2 * buf) * U_XT;
+      uint16_t* xl = xh + U_XT;
+#pragma unroll
+      for (int r = 0; r < NV; ++r) {
+        const int i = lane + 32 * r;
+        if (i < U_XT) {
+          uint16_t h, l;
+          u_split_f16(v[r] * sx, h, l);
+          xh[i] = h;
+          xl[i] = l;
+        }
+      }
+      tc::fence_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&x_full[buf]);
+    }
+  } else if (warp == 4 || warp == 6) {
+    // ---------------- MMA issuers: warp 4 takes the even tiles (accumulator 0), warp 6 the odd ones ----------
+    // All lanes run the loop (warp-uniform operands stay in uniform registers); the elected lane issues.
+    const int buf = tc::uniform(warp == 4 ? 0 : 1);
+    const int ntl = tc::uniform((int)my_tiles);
+    const int nks = tc::uniform(a.ksteps);
+    const uint32_t tm = tc::uniform((int)tmem);
+    const uint32_t idesc = tc::make_idesc_f16(128, U_NJ, tc::kFmtF16, tc::kFmtF16);
+    const uint64_t bdesc = tc::make_smem_desc(16, 128);      // in-place Toeplitz view of the waveform tile
+    const uint32_t d = tm + (uint32_t)(buf * U_TM_D1);
+    const uint32_t xh_addr = tc::uniform((int)tc::smem_addr(xbuf + (2 * buf) * U_XT));
+    for (int it = buf; it < ntl; it += 2) {
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      ok = ok && tc::mbar_wait(&acc_empty[buf], par ^ 1);
+      ok = ok && tc::mbar_wait(&x_full[buf], par);
+      tc::fence_after_sync();
+      if (tc::elect_one()) {
+        uint32_t bh = xh_addr, bl = xh_addr + U_XT * 2;
+        uint32_t ah = tm + U_TM_WHI, al = tm + U_TM_WLO;
+        for (int q = 0; q < nks; ++q) {
+          const uint64_t dh = tc::desc_at(bdesc, bh), dl = tc::desc_at(bdesc, bl);
+          tc::mma_f16_ts(d, ah, dh, idesc, q > 0);
+          tc::mma_f16_ts(d, ah, dl, idesc, 1);
+          tc::mma_f16_ts(d, al, dh, idesc, 1);
+          bh += 32;  // 16 taps
+          bl += 32;
+          ah += 8;
+          al += 8;
+        }
+        tc::mma_commit(&x_empty[buf]);
+        tc::mma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+    }
+  } else if (warp < 4) {
+    // ---------------- epilogue: TMEM -> scale -> staging -> bulk stores -------------------------------------
+    const int m = tid, cl = m >> 3, r = m & 7;
+    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    const float wi = winv[cl];
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      const int64_t tile = slot + it * per_blk;
+      const int64_t b = tile / a.tiles_per_row;
+      const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
+      float* sbuf = stage + buf * (U_FB * U_PITCH);
+      float* srow = sbuf + cl * U_PITCH + r;
+      if (lane < 4) tc::bulk_wait_read<1>();   // the stores that read this staging buffer two tiles ago are done
+      tc::named_bar_sync(1, 128);
+      ok = ok && tc::mbar_wait(&acc_full[buf], par);
+      tc::fence_after_sync();
+      const float sc = xinv[it & 3] * wi;      // read before acc_empty is released (the slot is reused 4 tiles later)
+      const uint32_t d = tmem + lane_base + (uint32_t)(buf * U_TM_D1);
+#pragma unroll 1
+      for (int ch = 0; ch < 4; ++ch) {         // 4 x 32 columns; the last 16 of 128 are not part of the accumulator
+        uint32_t v[32];
+        tc::tmem_ld32(d + 32 * ch, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (32 * ch + jj < U_NJ) srow[8 * (32 * ch + jj)] = __uint_as_float(v[jj]) * sc;
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator may be overwritten
+      tc::fence_async_smem();
+      tc::named_bar_sync(1, 128);
+      if (lane < 4) {
+        const int row = 4 * warp + lane;
+        const int c = c0 + row;
+        if (c < C) {
+          const int64_t n = (T - t0) < U_TT ? (T - t0) : U_TT;
+          tc::bulk_store(a.y + (b * C + c) * T + t0, sbuf + row * U_PITCH, (uint32_t)(n * 4));
+        }
+        tc::bulk_commit();
+      }
+    }
+    if (lane < 4) tc::bulk_wait<0>();
+  }
+  if (!ok && lane == 0) *a.status = 1;
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, 512);
+}
+
+bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di) {
+  (void)C;
+  return K + 7 <= U_KS && T % 4 == 0 && y_dtype == SINC_DTYPE_F32 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
+         di.max_smem_optin >= U_SM_TOTAL + 1024;
+}
+
+cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
+                            const DeviceInfo& di, cudaStream_t st) {
+  FwdTc16Args a;
+  a.bank = bank;
+  a.x = x;
+  a.xsb = x_stride_b;
+  a.y = reinterpret_cast<float*>(y);
+  a.B = B;
+  a.T = T;
+  a.nblk = (bank.C + U_FB - 1) / U_FB;
+  a.ksteps = (bank.K + 7 + 15) / 16;
+  a.tiles_per_row = ceil_div64(T, U_TT);
+  a.ntiles = B * a.tiles_per_row;
+  a.status = tc_status_device_ptr();
+  if (!a.status) return cudaErrorInvalidSymbol;
+  int64_t per_blk = di.sm_count / a.nblk;
+  if (per_blk < 1) per_blk = 1;
+  if (per_blk > a.ntiles) per_blk = a.ntiles;
+  const int grid = (int)(per_blk * a.nblk);
+  const size_t smem = U_SM_TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
+  cudaError_t e = cudaFuncSetAttribute(fwd_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  fwd_tc16_kernel<<<grid, U_THREADS, smem, st>>>(a);
+  count_launch();
+  return cudaGetLastError();
+}
+
+}  // namespace sinc

@@ -111,7 +111,8 @@ TC_BWD_SHAPES = [
     (64, 251, 16000, 3, 4100),
     (64, 251, 8000, 5, 100),
     (64, 251, 8000, 2, 4),
-    (64, 251, 16000, 40, 2048),     # several tiles per CTA slot and more than one flush for some CTAs
+    (64, 251, 16000, 40, 2048),     # several tiles per CTA slot
+    (64, 251, 16000, 24, 32768),    # > 8 tiles per CTA: two accumulation windows (double-buffered flush) in grad-filter
     (8, 250, 8000, 2, 2048),
     (70, 31, 44100, 2, 776),
     (130, 9, 8000, 1, 600),
