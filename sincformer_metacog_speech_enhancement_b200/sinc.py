@@ -90,7 +90,7 @@ class SincConvFunction(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype):
+    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype, sync=None):
         lib = _lib.load()
         if not x.is_cuda:
             raise RuntimeError("SincConv1d (B200): input must be a CUDA tensor -- this implementation has no CPU path")
@@ -123,6 +123,7 @@ class SincConvFunction(torch.autograd.Function):
         ctx.save_for_backward(xd, low, band, win, nn_)
         ctx.attrs = (float(sample_rate), float(min_low_hz), float(min_band_hz))
         ctx.expose_grad_filters = getattr(SincConvFunction, "_expose_grad_filters", False)
+        ctx.sync = sync
         return y
 
     @staticmethod
@@ -149,18 +150,36 @@ class SincConvFunction(torch.autograd.Function):
         if need_x or need_p:
             fb = _bank(low, band, win, nn_, sr, min_low, min_band)
             ws, ws_bytes = _workspace(B, T, C, K, dev)
-            with torch.cuda.device(dev):
-                stream = torch.cuda.current_stream(dev).cuda_stream
-                rc = lib.sinc_backward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(g),
-                                       _dtype_code(g.dtype), _ptr(gx), _ptr(gp[0] if need_p else None),
-                                       _ptr(gp[1] if need_p else None), _ptr(gfilt), B, T, _ptr(ws), ws_bytes,
-                                       ctypes.c_void_p(stream))
-            _lib.check(rc, "sinc_backward")
+            xs0 = xd.stride(0) if B > 1 else T
+
+            def launch(want_x, want_p):
+                with torch.cuda.device(dev):
+                    stream = torch.cuda.current_stream(dev).cuda_stream
+                    rc = lib.sinc_backward(ctypes.byref(fb), _ptr(xd), xs0, _ptr(g), _dtype_code(g.dtype),
+                                           _ptr(gx if want_x else None), _ptr(gp[0] if want_p else None),
+                                           _ptr(gp[1] if want_p else None), _ptr(gfilt if want_p else None), B, T,
+                                           _ptr(ws), ws_bytes, ctypes.c_void_p(stream))
+                _lib.check(rc, "sinc_backward")
+
+            sync = ctx.sync
+            if need_p and sync is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
+                # data-parallel: parameter gradients first, their 2*C-float all-reduce (the only exchange of the
+                # path) is then in flight on NCCL's stream while grad-input runs
+                group, average = sync
+                launch(False, True)
+                work = torch.distributed.all_reduce(gp, op=torch.distributed.ReduceOp.SUM, group=group, async_op=True)
+                if need_x:
+                    launch(True, False)
+                work.wait()
+                if average:
+                    gp /= torch.distributed.get_world_size(group)
+            else:
+                launch(need_x, need_p)
         if gfilt is not None:
             SincConvFunction._last_grad_filters = gfilt
         g_low = gp[0] if need_p and ctx.needs_input_grad[1] else None
         g_band = gp[1] if need_p and ctx.needs_input_grad[2] else None
-        return gx, g_low, g_band, None, None, None, None, None, None
+        return gx, g_low, g_band, None, None, None, None, None, None, None
 
 
 class SincConv1d(nn.Module):
@@ -220,8 +239,20 @@ class SincConv1d(nn.Module):
             waveform = waveform.unsqueeze(0)
             unbatched = True
         y = SincConvFunction.apply(waveform, self.low_hz_, self.band_hz_, self.window, self.n_,
-                                   self.sample_rate, self.min_low_hz, self.min_band_hz, self.out_dtype)
+                                   self.sample_rate, self.min_low_hz, self.min_band_hz, self.out_dtype,
+                                   getattr(self, "_grad_sync", None))
         return y.squeeze(0) if unbatched else y
+
+    def enable_grad_sync(self, group=None, average=False):
+        """Data-parallel use WITHOUT DistributedDataParallel: all-reduce (SUM, or mean) the 2*out_channels
+        parameter gradients inside backward, overlapped with the grad-input kernel.  Do not combine with DDP or
+        with ``allreduce_filter_grads`` (the gradients would be reduced twice).  ``disable_grad_sync`` undoes it."""
+        self._grad_sync = (group, bool(average))
+        return self
+
+    def disable_grad_sync(self):
+        self._grad_sync = None
+        return self
 
     @torch.no_grad()
     def filters(self):

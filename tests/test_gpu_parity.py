@@ -201,6 +201,32 @@ def test_bf16_output_mode():
     assert (dut.band_hz_.grad.cpu().double() - o64["g_band"]).abs().max() <= TOL_P * o64["g_band"].abs().max() + fb
 
 
+def test_grad_sync_inside_backward_single_rank_nccl():
+    """enable_grad_sync: parameter gradients first, all-reduce in flight during grad-input.  With a one-rank NCCL
+    group the result must equal the unsynchronised gradients bit for bit (SUM over one rank), and the mean too."""
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1,
+                                device_id=dev())
+        created = True
+    try:
+        _, dut = make_pair(64, 251, 16000)
+        gen = torch.Generator().manual_seed(21)
+        x, g = torch.randn(3, 1, 4000, generator=gen), torch.randn(3, 64, 4000, generator=gen)
+        ref = run_dut(dut, x, g, expose=False)
+        dut.enable_grad_sync()
+        a = run_dut(dut, x, g, expose=False)
+        dut.enable_grad_sync(average=True)
+        b = run_dut(dut, x, g, expose=False)
+        dut.disable_grad_sync()
+        for k in ("y", "gx", "g_low", "g_band"):
+            assert torch.equal(a[k], ref[k]) and torch.equal(b[k], ref[k]), k
+    finally:
+        if created:
+            dist.destroy_process_group()
+
+
 def test_bitwise_reproducible():
     _, dut = make_pair(64, 251, 16000)
     gen = torch.Generator().manual_seed(3)

@@ -19,10 +19,12 @@ from test_gpu_parity import make_pair, run_dut, check_against, dev, TOL_Y
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture
-def tc_engine():
-    sb.set_engine("tc")
-    yield
+@pytest.fixture(params=["tc", "tc_tf32"])
+def tc_engine(request):
+    """Both tensor-core engines: 'tc' (16-bit split operands: scaled fp16 forward, bf16 hi/mid backward) and
+    'tc_tf32' (3xTF32 split in every pass)."""
+    sb.set_engine(request.param)
+    yield request.param
     sb.set_engine("auto")
 
 
@@ -121,8 +123,9 @@ TC_BWD_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("engine", ["tc", "tc_tf32"])
 @pytest.mark.parametrize("C,K,sr,B,T", TC_BWD_SHAPES)
-def test_tc_backward_vs_oracle(C, K, sr, B, T):
+def test_tc_backward_vs_oracle(engine, C, K, sr, B, T):
     orc, dut = make_pair(C, K, sr)
     gen = torch.Generator().manual_seed(C * 13 + T)
     with torch.no_grad():
@@ -140,7 +143,7 @@ def test_tc_backward_vs_oracle(C, K, sr, B, T):
     SincConvFunction._expose_grad_filters = True
     try:
         y = dut(xd)
-        sb.set_engine("tc")
+        sb.set_engine(engine)
         y.backward(g.to(dev()))
         torch.cuda.synchronize()
         mask = lib.sinc_last_engine_mask()
@@ -149,10 +152,12 @@ def test_tc_backward_vs_oracle(C, K, sr, B, T):
         SincConvFunction._expose_grad_filters = False
     out = dict(y=y.detach().cpu(), gx=xd.grad.cpu(), gfilt=SincConvFunction._last_grad_filters.cpu(),
                g_low=dut.low_hz_.grad.cpu(), g_band=dut.band_hz_.grad.cpu())
-    if T % 4 == 0 and K <= 312:
+    if T % 4 == 0 and K <= (256 if engine == "tc" else 312):
         assert mask & 4, "grad-filter did not run on the tcgen05 engine"
+        assert bool(mask & 32) == (engine == "tc"), "grad-filter: wrong operand-split variant"
     if C <= 64 and K <= 256:
         assert mask & 2, "grad-input did not run on the tcgen05 engine"
+        assert bool(mask & 16) == (engine == "tc" and T % 4 == 0), "grad-input: wrong operand-split variant"
     assert tc_status() == 0
     check_against(orc, out, x, g)
 
