@@ -150,7 +150,7 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   const bool use_tc = want_tc && tc_ok && !use_tc16;
   cudaError_t e;
   if (use_tc16) {
-    e = launch_fwd_tc16(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
+    e = launch_fwd_tc16(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
   } else if (use_tc) {
     e = launch_fwd_tc(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
   } else {
@@ -190,7 +190,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
     if (use_tc16)
-      e = launch_bwd_input_tc16(bank, grad_y, grad_x, B, T, di, st);
+      e = launch_bwd_input_tc16(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
     else if (use_tc)
       e = launch_bwd_input_tc(bank, grad_y, grad_x, B, T, di, st);
     else
@@ -211,7 +211,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
     if (use_tc16)
-      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
+      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
     else if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else

@@ -96,14 +96,14 @@ cudaError_t launch_bwd_input_tc(const Bank& bank, const void* gy, float* gx, int
 
 // 16-bit split variants (bf16 hi/mid, three kind::f16 MMAs): sinc_tc16_*.cu
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
-cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, float* gx, int64_t B, int64_t T,
+cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
                                   const DeviceInfo& di, cudaStream_t st);
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di);
-cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
-                            const DeviceInfo& di, cudaStream_t st);
+cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype, int64_t B,
+                            int64_t T, const DeviceInfo& di, cudaStream_t st);
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 size_t tc16_bwd_filter_partial_bytes(int C);
-cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy,
+cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
                                    cudaStream_t st);
 

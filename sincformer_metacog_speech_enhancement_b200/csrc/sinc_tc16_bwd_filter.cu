@@ -54,10 +54,30 @@ constexpr int F2_SM_TOTAL = F2_SM_BAR + 512;
 static_assert(28 + F2_GSTAGES <= 32, "barrier table: tmem_slot lives at bars + 32");
 static_assert((F2_XLEN * 2) % 16 == 0, "waveform copies must stay 16-byte aligned");
 
+// grad_y element type: fp32 (split into bf16 hi + mid) or bf16 (bf16-output mode: already exact, no mid piece and
+// one MMA fewer per product).  `vec` = 4 consecutive samples of a staged row.
+template <bool GB>
+struct F2G;
+template <>
+struct F2G<false> {
+  using vec = float4;
+  static constexpr int esz = 4;
+  static constexpr int pitch = F2_GPITCH;
+  __device__ static vec zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <>
+struct F2G<true> {
+  using vec = uint2;
+  static constexpr int esz = 2;
+  static constexpr int pitch = F2_GSAMP * 2 + 16;  // 16 mod 128: the LDS.64 of a half-warp (8 filters x 2 interleaves)
+                                                   // cover 16 distinct 8-byte slots
+  __device__ static vec zero() { return make_uint2(0u, 0u); }
+};
+
 struct BwdFilterTc16Args {
   const float* x;
   int64_t xsb;
-  const float* g;
+  const void* g;
   int64_t B, T;
   int C, K;
   float* partials;  // [gridDim.x / nblk][nblk][128][F2_DCOLS]
@@ -80,7 +100,11 @@ __device__ __forceinline__ int f2_ksteps(int64_t left, bool last) {
   return (span + 15) / 16;
 }
 
+template <bool GB>
 __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const BwdFilterTc16Args a) {
+  using G = F2G<GB>;
+  using gvec = typename G::vec;
+  constexpr int GPITCH = G::pitch;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint16_t* xs = reinterpret_cast<uint16_t*>(smem + F2_SM_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_SM_BAR);
@@ -148,18 +172,25 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     const int c = c0 + cl;
     const bool row_valid = c < C;
     const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 halo = zero4;  // the 4 samples before the current stage (h = 1 rows start 4 samples early)
+    const gvec zero4 = G::zero();
+    gvec halo = zero4;  // the 4 samples before the current stage (h = 1 rows start 4 samples early)
+    const uint8_t* gbytes = reinterpret_cast<const uint8_t*>(a.g);
     int64_t cc0 = 0;      // ring slots (chunks of F2_KPS K-steps) before the current tile
     int64_t gs = 0;       // staging stages consumed so far
-    auto emit = [&](const float4 (&v)[4 * F2_KPS], int64_t cc) {  // F2_KPS K-steps of this row -> one TMEM ring slot
+    auto emit = [&](const gvec (&v)[4 * F2_KPS], int64_t cc) {  // F2_KPS K-steps of this row -> one TMEM ring slot
       const int s = (int)(cc & (F2_RING - 1));
       const uint32_t par = (uint32_t)((cc / F2_RING) & 1);
       uint32_t hi[8 * F2_KPS], mid[8 * F2_KPS];
 #pragma unroll
       for (int j = 0; j < 4 * F2_KPS; ++j) {
-        f2_split_bf16x2(v[j].x, v[j].y, hi[2 * j], mid[2 * j]);
-        f2_split_bf16x2(v[j].z, v[j].w, hi[2 * j + 1], mid[2 * j + 1]);
+        if constexpr (GB) {  // bf16 pairs are already packed in memory order (even sample in the low half)
+          hi[2 * j] = v[j].x;
+          hi[2 * j + 1] = v[j].y;
+          mid[2 * j] = mid[2 * j + 1] = 0u;
+        } else {
+          f2_split_bf16x2(v[j].x, v[j].y, hi[2 * j], mid[2 * j]);
+          f2_split_bf16x2(v[j].z, v[j].w, hi[2 * j + 1], mid[2 * j + 1]);
+        }
       }
       ok = ok && tc::mbar_wait(&a_empty[s], par ^ 1);
       tc::fence_after_sync();
@@ -173,7 +204,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           tm8[e] = mid[8 * kk + e];
         }
         tc::tmem_st8(dst + 16 * kk, th);
-        tc::tmem_st8(dst + 16 * kk + 8, tm8);
+        if constexpr (!GB) tc::tmem_st8(dst + 16 * kk + 8, tm8);
       }
       tc::tmem_st_wait();
       tc::fence_before_sync();
@@ -192,35 +223,35 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
       if (ti == 0) {
         halo = zero4;  // utterance start: t < 0
       } else if (it == 0) {  // this CTA starts in the middle of an utterance: fetch the 4 samples before its first tile
-        halo = (h && row_valid) ? __ldg(reinterpret_cast<const float4*>(a.g + (b * C + c) * T + tb - 4)) : zero4;
+        halo = (h && row_valid) ? __ldg(reinterpret_cast<const gvec*>(gbytes + ((b * C + c) * T + tb - 4) * G::esz)) : zero4;
       }
       for (int st = 0; st < nstg; ++st) {
         const int gb = (int)(gs & (F2_GSTAGES - 1));
         ok = ok && tc::mbar_wait(&g_full[gb], (uint32_t)((gs / F2_GSTAGES) & 1));
-        const uint8_t* rowp = gst + gb * F2_GSTAGE_BYTES + cl * F2_GPITCH;
+        const uint8_t* rowp = gst + gb * F2_GSTAGE_BYTES + cl * GPITCH;
         const int64_t ts = tb + (int64_t)F2_GSAMP * st;
 #pragma unroll
         for (int u = 0; u < 8 / F2_KPS / 2; ++u) {
           const int pch = grp + 2 * u;                 // chunk of the stage; chunk ch of the tile belongs to group ch & 1
           const int ch = (8 / F2_KPS) * st + pch;
           if (F2_KPS * ch < nq) {
-            float4 v[4 * F2_KPS];
+            gvec v[4 * F2_KPS];
 #pragma unroll
             for (int i = 0; i < 4 * F2_KPS; ++i) {
               const int off = 16 * F2_KPS * pch - 4 * h + 4 * i;  // sample offset within the stage (-4 only for pch = 0, h = 1)
               const int64_t tj = ts + off;
-              float4 w;
+              gvec w;
               if (pch == 0 && i == 0)
-                w = h ? halo : *reinterpret_cast<const float4*>(rowp);
+                w = h ? halo : *reinterpret_cast<const gvec*>(rowp);
               else
-                w = *reinterpret_cast<const float4*>(rowp + 4 * off);
+                w = *reinterpret_cast<const gvec*>(rowp + G::esz * off);
               v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
             }
             emit(v, cc0 + ch);
           }
         }
         if (h) {  // carry the last 4 samples of the row into the next stage
-          const float4 w = *reinterpret_cast<const float4*>(rowp + 4 * (F2_GSAMP - 4));
+          const gvec w = *reinterpret_cast<const gvec*>(rowp + G::esz * (F2_GSAMP - 4));
           halo = (row_valid && ts + F2_GSAMP - 4 < T) ? w : zero4;
         }
         __syncwarp();
@@ -228,7 +259,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         ++gs;
       }
       if (nq > 8 * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
-        float4 v[4 * F2_KPS];
+        gvec v[4 * F2_KPS];
 #pragma unroll
         for (int i = 0; i < 4 * F2_KPS; ++i) v[i] = zero4;
         if (h) v[0] = halo;
@@ -291,8 +322,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
               tc::mma_f16_ts(d0 + F2_N, ah, bh1, idesc, acc0);
               tc::mma_f16_ts(d0, ah, bm0, idesc, 1);
               tc::mma_f16_ts(d0 + F2_N, ah, bm1, idesc, 1);
-              tc::mma_f16_ts(d0, am, bh0, idesc, 1);
-              tc::mma_f16_ts(d0 + F2_N, am, bh1, idesc, 1);
+              if constexpr (!GB) {  // bf16 grad_y has no mid piece
+                tc::mma_f16_ts(d0, am, bh0, idesc, 1);
+                tc::mma_f16_ts(d0 + F2_N, am, bh1, idesc, 1);
+              }
             }
             tc::mma_commit(&a_empty[s]);
           }
@@ -368,15 +401,15 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         const int64_t left = T - tb;
         const int span = (int)(left < F2_TILE ? left : F2_TILE);
         const int nstg = (span + F2_GSAMP - 1) / F2_GSAMP;
-        const float* src_tile = a.g + (brow * C + c0) * T + tb;
+        const uint8_t* src_tile = reinterpret_cast<const uint8_t*>(a.g) + ((brow * C + c0) * T + tb) * G::esz;
         for (int st = 0; st < nstg; ++st) {
           const int gb = gs & (F2_GSTAGES - 1);
           ok = ok && tc::mbar_wait(&g_empty[gb], (uint32_t)(((gs / F2_GSTAGES) & 1) ^ 1));
           const int nsamp = span - F2_GSAMP * st < F2_GSAMP ? span - F2_GSAMP * st : F2_GSAMP;
-          const uint32_t bytes = (uint32_t)nsamp * 4;  // T % 4 == 0: a multiple of 16
+          const uint32_t bytes = (uint32_t)nsamp * G::esz;  // T % 4 == 0 (fp32) / T % 8 == 0 (bf16): a multiple of 16
           if (tc::elect_one()) {
             tc::mbar_expect_tx(&g_full[gb], (uint32_t)nrows * bytes);
-            const float* src = src_tile + F2_GSAMP * st;
+            const uint8_t* src = src_tile + (int64_t)F2_GSAMP * st * G::esz;
             uint32_t dst = gst0 + gb * F2_GSTAGE_BYTES;
             const uint32_t bar = tc::smem_addr(&g_full[gb]);
 #pragma unroll 4
@@ -384,8 +417,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
               asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                            "l"(src), "r"(bytes), "r"(bar)
                            : "memory");
-              src += T;
-              dst += F2_GPITCH;
+              src += T * G::esz;
+              dst += GPITCH;
             }
           }
           __syncwarp();
@@ -441,8 +474,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
 
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
   (void)C;
-  return K <= 256 && T % 4 == 0 && g_dtype == SINC_DTYPE_F32 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
-         di.max_smem_optin >= F2_SM_TOTAL + 1024;
+  const bool shape_ok = g_dtype == SINC_DTYPE_F32 ? T % 4 == 0 : (g_dtype == SINC_DTYPE_BF16 && T % 8 == 0);
+  return K <= 256 && shape_ok && reinterpret_cast<uintptr_t>(g) % 16 == 0 && di.max_smem_optin >= F2_SM_TOTAL + 1024;
 }
 
 size_t tc16_bwd_filter_partial_bytes(int C) {
@@ -450,13 +483,13 @@ size_t tc16_bwd_filter_partial_bytes(int C) {
   return (size_t)kMaxPartialSlots * nblk * 128 * F2_DCOLS * sizeof(float);
 }
 
-cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy,
+cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
                                    cudaStream_t st) {
   BwdFilterTc16Args a;
   a.x = x;
   a.xsb = x_stride_b;
-  a.g = reinterpret_cast<const float*>(gy);
+  a.g = gy;
   a.B = B;
   a.T = T;
   a.C = bank.C;
@@ -473,9 +506,10 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
   if (per_blk > kMaxPartialSlots) per_blk = kMaxPartialSlots;
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = F2_SM_TOTAL + 1024;
-  cudaError_t e = cudaFuncSetAttribute(bwd_filter_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_filter_tc16_kernel<true> : bwd_filter_tc16_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  bwd_filter_tc16_kernel<<<grid, F2_THREADS, smem, st>>>(a);
+  kern<<<grid, F2_THREADS, smem, st>>>(a);
   count_launch();
   *slots_used = (int)per_blk;
   return cudaGetLastError();

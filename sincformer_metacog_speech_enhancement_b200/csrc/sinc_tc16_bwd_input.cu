@@ -29,6 +29,8 @@
 // at the start of each run.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "sinc_internal.h"
 #include "sinc_synth.cuh"
 #include "sinc_tc.cuh"
@@ -57,7 +59,7 @@ static_assert(H2_SM_S % 16 == 0 && H2_SM_OUT % 16 == 0, "alignment");
 
 struct BwdInputTc16Args {
   Bank bank;
-  const float* g;
+  const void* g;           // fp32, or bf16 (bf16-output mode: exact in one bf16 piece -- no mid planes, one MMA fewer)
   float* gx;
   int64_t B, T;
   int64_t blocks_per_row;  // ceil(T / 128)
@@ -72,6 +74,7 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, u
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid) : "f"(v1 - h1), "f"(v0 - h0));
 }
 
+template <bool GB>
 __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const BwdInputTc16Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* ring = smem + H2_SM_G;
@@ -178,16 +181,21 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
       const int pw = warp - 8;
       const int fg = lane & 3, pg = lane >> 2;  // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups
       const int n0 = 32 * pw + 4 * pg;  // first of this thread's four columns within the stage
-      const float* gb = a.g + (b * C) * T;
-      float4 vv[16];
+      using gvec = typename std::conditional<GB, uint2, float4>::type;   // 4 consecutive positions of one filter row
+      constexpr int ESZ = GB ? 2 : 4;
+      const uint8_t* gb = reinterpret_cast<const uint8_t*>(a.g) + (b * C) * T * ESZ;
+      gvec vv[16];
       auto load_stage = [&](int64_t p) {  // p = position of column n0 (a multiple of 4; T % 4 == 0)
         const bool in = p >= 0 && p < T;
-        const float* q = gb + (in ? p : 0) + (int64_t)(8 * fg) * T;  // one running row pointer: no address array
+        const uint8_t* q = gb + ((in ? p : 0) + (int64_t)(8 * fg) * T) * ESZ;  // one running row pointer: no address array
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int c = 8 * fg + (j & 7) + 32 * (j >> 3);
-          vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          q += (j == 7) ? 25 * T : T;
+          if constexpr (GB)
+            vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const uint2*>(q)) : make_uint2(0u, 0u);
+          else
+            vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          q += ((j == 7) ? 25 * T : T) * ESZ;
         }
       };
       for (int i = 0; i < nst; ++i) {
@@ -200,12 +208,21 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
           if (pw == 0) {  // run start: the halo row (position c0 - 1) has no previous stage; lane = filter pair
             const int64_t p = c0 - 1;
             const bool in = p >= 0 && p < T;
-            const float w0 = (in && 2 * lane < C) ? __ldg(gb + (int64_t)(2 * lane) * T + p) : 0.f;
-            const float w1 = (in && 2 * lane + 1 < C) ? __ldg(gb + (int64_t)(2 * lane + 1) * T + p) : 0.f;
             uint32_t h, m;
-            split_bf16x2(w0, w1, h, m);
+            if constexpr (GB) {
+              const uint16_t* g16 = reinterpret_cast<const uint16_t*>(gb);
+              const uint32_t w0 = (in && 2 * lane < C) ? __ldg(g16 + (int64_t)(2 * lane) * T + p) : 0u;
+              const uint32_t w1 = (in && 2 * lane + 1 < C) ? __ldg(g16 + (int64_t)(2 * lane + 1) * T + p) : 0u;
+              h = w0 | (w1 << 16);
+              m = 0u;
+            } else {
+              const float* g32 = reinterpret_cast<const float*>(gb);
+              const float w0 = (in && 2 * lane < C) ? __ldg(g32 + (int64_t)(2 * lane) * T + p) : 0.f;
+              const float w1 = (in && 2 * lane + 1 < C) ? __ldg(g32 + (int64_t)(2 * lane + 1) * T + p) : 0.f;
+              split_bf16x2(w0, w1, h, m);
+            }
             *reinterpret_cast<uint32_t*>(base + (lane >> 2) * H2_PLANE + (lane & 3) * 4) = h;
-            *reinterpret_cast<uint32_t*>(base + (8 + (lane >> 2)) * H2_PLANE + (lane & 3) * 4) = m;
+            if constexpr (!GB) *reinterpret_cast<uint32_t*>(base + (8 + (lane >> 2)) * H2_PLANE + (lane & 3) * 4) = m;
           }
           load_stage(c0 + n0);
         }
@@ -215,21 +232,31 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         for (int s2 = 0; s2 < 2; ++s2) {
           const int cq = fg + 4 * s2;
           if (cq < 2 * ncb) {
-            const float4* v8 = vv + 8 * s2;
+            const gvec* v8 = vv + 8 * s2;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              auto comp = [&](const float4& f) { return o == 0 ? f.x : o == 1 ? f.y : o == 2 ? f.z : f.w; };
               uint4 h, m;
-              split_bf16x2(comp(v8[0]), comp(v8[1]), h.x, m.x);
-              split_bf16x2(comp(v8[2]), comp(v8[3]), h.y, m.y);
-              split_bf16x2(comp(v8[4]), comp(v8[5]), h.z, m.z);
-              split_bf16x2(comp(v8[6]), comp(v8[7]), h.w, m.w);
+              if constexpr (GB) {
+                // bf16 inputs: pick the 16-bit sample o of two filter rows and pack them (even filter in the low half)
+                auto pk = [&](const uint2& lo, const uint2& hi2) {
+                  const uint32_t wl = o < 2 ? lo.x : lo.y, wh = o < 2 ? hi2.x : hi2.y;
+                  return __byte_perm(wl, wh, (o & 1) ? 0x7632 : 0x5410);
+                };
+                h = make_uint4(pk(v8[0], v8[1]), pk(v8[2], v8[3]), pk(v8[4], v8[5]), pk(v8[6], v8[7]));
+                m = make_uint4(0u, 0u, 0u, 0u);
+              } else {
+                auto comp = [&](const float4& f) { return o == 0 ? f.x : o == 1 ? f.y : o == 2 ? f.z : f.w; };
+                split_bf16x2(comp(v8[0]), comp(v8[1]), h.x, m.x);
+                split_bf16x2(comp(v8[2]), comp(v8[3]), h.y, m.y);
+                split_bf16x2(comp(v8[4]), comp(v8[5]), h.z, m.z);
+                split_bf16x2(comp(v8[6]), comp(v8[7]), h.w, m.w);
+              }
               uint8_t* dst = base + cq * H2_PLANE + (n0 + o + 1) * 16;
               *reinterpret_cast<uint4*>(dst) = h;
-              *reinterpret_cast<uint4*>(dst + 8 * H2_PLANE) = m;
+              if constexpr (!GB) *reinterpret_cast<uint4*>(dst + 8 * H2_PLANE) = m;
               if (o == 3 && dup) {
                 *reinterpret_cast<uint4*>(dup + cq * H2_PLANE) = h;
-                *reinterpret_cast<uint4*>(dup + (8 + cq) * H2_PLANE) = m;
+                if constexpr (!GB) *reinterpret_cast<uint4*>(dup + (8 + cq) * H2_PLANE) = m;
               }
             }
           }
@@ -272,7 +299,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
               for (int cb = 0; cb < ncbu; ++cb) {
                 const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
                 tc::mma_f16_ts(d, ah, dh, idesc, acc);
-                tc::mma_f16_ts(d, ah, dm, idesc, 1);
+                if constexpr (!GB) tc::mma_f16_ts(d, ah, dm, idesc, 1);  // bf16 grad_y has no mid planes
                 tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
                 acc = 1;
                 ah += 8;
@@ -377,15 +404,15 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
 }
 
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
-  return C <= 64 && K <= 256 && T % 4 == 0 && g_dtype == SINC_DTYPE_F32 && reinterpret_cast<uintptr_t>(g) % 16 == 0 &&
-         di.max_smem_optin >= H2_SM_TOTAL + 1024;
+  return C <= 64 && K <= 256 && T % 4 == 0 && (g_dtype == SINC_DTYPE_F32 || g_dtype == SINC_DTYPE_BF16) &&
+         reinterpret_cast<uintptr_t>(g) % 16 == 0 && di.max_smem_optin >= H2_SM_TOTAL + 1024;
 }
 
-cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, float* gx, int64_t B, int64_t T,
+cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
                                   const DeviceInfo& di, cudaStream_t st) {
   BwdInputTc16Args a;
   a.bank = bank;
-  a.g = reinterpret_cast<const float*>(gy);
+  a.g = gy;
   a.gx = gx;
   a.B = B;
   a.T = T;
@@ -395,9 +422,10 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, float* gx, i
   if (!a.status) return cudaErrorInvalidSymbol;
   const int grid = (int)(a.nblocks < di.sm_count ? a.nblocks : di.sm_count);
   const size_t smem = H2_SM_TOTAL + 1024;
-  cudaError_t e = cudaFuncSetAttribute(bwd_input_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_input_tc16_kernel<true> : bwd_input_tc16_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  bwd_input_tc16_kernel<<<grid, H2_THREADS, smem, st>>>(a);
+  kern<<<grid, H2_THREADS, smem, st>>>(a);
   count_launch();
   return cudaGetLastError();
 }

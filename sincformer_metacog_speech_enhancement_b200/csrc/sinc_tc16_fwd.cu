@@ -23,6 +23,7 @@
 // Warp roles (224 threads): warps 0-3 epilogue (TMEM -> scale -> phase-interleaved staging -> 1-D bulk stores
 // of 3.5 KB rows), warps 4 and 6 MMA issuers (even / odd tiles, warp-uniform issue loops), warp 5 waveform
 // producer (global -> max -> scale -> fp16 hi/lo -> smem).
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #include "sinc_internal.h"
@@ -52,7 +53,7 @@ struct FwdTc16Args {
   Bank bank;
   const float* x;
   int64_t xsb;
-  float* y;
+  void* y;             // fp32 or bf16 (bf16-output mode: fp32 accumulators, rounded once in the epilogue)
   int64_t B, T;
   int nblk;            // filter blocks of 16
   int ksteps;          // ceil((K + 7) / 16) <= 17
@@ -82,7 +83,10 @@ __device__ __forceinline__ void u_split_f16(float v, uint16_t& hi, uint16_t& lo)
   lo = __half_as_ushort(l);
 }
 
+template <bool OB>
 __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Args a) {
+  constexpr int ESZ = OB ? 2 : 4;                 // bytes per output element
+  constexpr int PITCHB = U_PITCH * ESZ;           // staging row pitch in bytes (32 resp. 16 mod 128: conflict free)
   extern __shared__ __align__(1024) uint8_t smem[];
   uint16_t* xbuf = reinterpret_cast<uint16_t*>(smem + U_SM_X);  // [buf][hi/lo][U_XT]
   float* stage = reinterpret_cast<float*>(smem + U_SM_STAGE);   // [2][U_FB][U_PITCH]
@@ -256,8 +260,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       const int64_t tile = slot + it * per_blk;
       const int64_t b = tile / a.tiles_per_row;
       const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
-      float* sbuf = stage + buf * (U_FB * U_PITCH);
-      float* srow = sbuf + cl * U_PITCH + r;
+      uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage) + buf * (U_FB * U_PITCH * 4);
+      uint8_t* srow = sbuf + cl * PITCHB + r * ESZ;
       if (lane < 4) tc::bulk_wait_read<1>();   // the stores that read this staging buffer two tiles ago are done
       tc::named_bar_sync(1, 128);
       ok = ok && tc::mbar_wait(&acc_full[buf], par);
@@ -271,7 +275,13 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
         tc::tmem_ld_wait();
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
-          if (32 * ch + jj < U_NJ) srow[8 * (32 * ch + jj)] = __uint_as_float(v[jj]) * sc;
+          if (32 * ch + jj < U_NJ) {
+            const float yv = __uint_as_float(v[jj]) * sc;
+            if constexpr (OB)
+              *reinterpret_cast<__nv_bfloat16*>(srow + 8 * (32 * ch + jj) * ESZ) = __float2bfloat16_rn(yv);
+            else
+              *reinterpret_cast<float*>(srow + 8 * (32 * ch + jj) * ESZ) = yv;
+          }
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -283,7 +293,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
         const int c = c0 + row;
         if (c < C) {
           const int64_t n = (T - t0) < U_TT ? (T - t0) : U_TT;
-          tc::bulk_store(a.y + (b * C + c) * T + t0, sbuf + row * U_PITCH, (uint32_t)(n * 4));
+          tc::bulk_store(reinterpret_cast<uint8_t*>(a.y) + ((b * C + c) * T + t0) * ESZ, sbuf + row * PITCHB,
+                         (uint32_t)(n * ESZ));
         }
         tc::bulk_commit();
       }
@@ -298,17 +309,17 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
 
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di) {
   (void)C;
-  return K + 7 <= U_KS && T % 4 == 0 && y_dtype == SINC_DTYPE_F32 && reinterpret_cast<uintptr_t>(y) % 16 == 0 &&
-         di.max_smem_optin >= U_SM_TOTAL + 1024;
+  const bool shape_ok = y_dtype == SINC_DTYPE_F32 ? T % 4 == 0 : (y_dtype == SINC_DTYPE_BF16 && T % 8 == 0);
+  return K + 7 <= U_KS && shape_ok && reinterpret_cast<uintptr_t>(y) % 16 == 0 && di.max_smem_optin >= U_SM_TOTAL + 1024;
 }
 
-cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
-                            const DeviceInfo& di, cudaStream_t st) {
+cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype, int64_t B,
+                            int64_t T, const DeviceInfo& di, cudaStream_t st) {
   FwdTc16Args a;
   a.bank = bank;
   a.x = x;
   a.xsb = x_stride_b;
-  a.y = reinterpret_cast<float*>(y);
+  a.y = y;
   a.B = B;
   a.T = T;
   a.nblk = (bank.C + U_FB - 1) / U_FB;
@@ -322,9 +333,10 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
   if (per_blk > a.ntiles) per_blk = a.ntiles;
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = U_SM_TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-  cudaError_t e = cudaFuncSetAttribute(fwd_tc16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  auto kern = y_dtype == SINC_DTYPE_BF16 ? fwd_tc16_kernel<true> : fwd_tc16_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  fwd_tc16_kernel<<<grid, U_THREADS, smem, st>>>(a);
+  kern<<<grid, U_THREADS, smem, st>>>(a);
   count_launch();
   return cudaGetLastError();
 }

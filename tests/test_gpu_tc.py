@@ -176,3 +176,34 @@ def test_tc_backward_long_accumulation(tc_engine):
     # still an order of magnitude inside the 1e-4 gate
     assert max_rel(out["gfilt"], o64["gfilt"]) <= 5e-5
     assert max_rel(out["g_low"], o64["g_low"]) <= 1e-4 and max_rel(out["g_band"], o64["g_band"]) <= 1e-4
+
+
+@pytest.mark.parametrize("B,T", [(3, 4096), (2, 10240), (5, 104)])
+def test_tc16_bf16_activation_mode(B, T):
+    """bf16-output mode on the 16-bit tensor-core kernels: bf16 y (rounded once from fp32 accumulators) and bf16
+    grad_y (exact in one bf16 piece: two MMAs per product instead of three)."""
+    orc, dut = make_pair(64, 251, 16000, out_dtype=torch.bfloat16)
+    gen = torch.Generator().manual_seed(B * 1000 + T)
+    x = torch.randn(B, 1, T, generator=gen)
+    g = torch.randn(B, 64, T, generator=gen).bfloat16().float()
+    sb.set_engine("tc")
+    try:
+        xd = x.to(dev()).requires_grad_(True)
+        y = dut(xd)
+        y.backward(g.to(dev()).bfloat16())
+        torch.cuda.synchronize()
+        mask = _lib.load().sinc_last_engine_mask()
+    finally:
+        sb.set_engine("auto")
+    assert y.dtype == torch.bfloat16 and tc_status() == 0
+    assert mask & 8 and mask & 16 and mask & 32, "bf16 mode did not run on the 16-bit tensor-core kernels"
+    ref = orc(x).detach()
+    err = (y.float().cpu() - ref).abs()
+    assert bool((err <= 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all())
+    o32 = O.full_backward(orc, x, g, torch.float32)
+    o64 = O.full_backward(orc, x, g, torch.float64)
+    assert max_rel(xd.grad.cpu(), o32["gx"]) <= 1e-4
+    from test_gpu_parity import param_floor
+    fl, fb = param_floor(orc, o64["gfilt"].numpy())
+    assert (dut.low_hz_.grad.cpu().double() - o64["g_low"]).abs().max() <= 1e-4 * o64["g_low"].abs().max() + fl
+    assert (dut.band_hz_.grad.cpu().double() - o64["g_band"]).abs().max() <= 1e-4 * o64["g_band"].abs().max() + fb
