@@ -55,6 +55,15 @@ def main():
         with torch.no_grad():
             msf = ev_time(lambda: F.conv1d(x, w, stride=1, padding=K // 2), reps=5, warm=2)
         out[f"cudnn_conv1d_fwd_ms_tf32_{tf32}"] = msf
+    # HBM write-only and read-only streams (the forward is a 393 MB write stream, the backward kernels read streams)
+    buf = torch.empty(B * C * T, device="cuda")
+    ms_w = ev_time(lambda: buf.fill_(1.0))
+    out["hbm_write_only_gbs"] = buf.numel() * 4 / ms_w / 1e6
+    ms_r = ev_time(lambda: buf.sum())
+    out["hbm_read_only_gbs_torch_sum"] = buf.numel() * 4 / ms_r / 1e6
+    dst = torch.empty_like(buf)
+    ms_c = ev_time(lambda: dst.copy_(buf))
+    out["hbm_copy_gbs"] = 2 * buf.numel() * 4 / ms_c / 1e6
     print(json.dumps(out))
 
 
