@@ -17,7 +17,7 @@
 //
 // On-chip budget per CTA (one CTA per SM, 16 filters; CTAs alternate between the filter blocks):
 //     TMEM  D0 [0,112)  D1 [128,240)  W'_hi [240,376)  W'_lo [376,512)   (16-bit operands: two taps per column)
-//     SMEM  2 x (x_hi, x_lo) tiles 9 KB | 2 x output staging 57 KB (double-buffered against the bulk stores)
+//     SMEM  2 x (x_hi, x_lo) tiles 9 KB | 3 x output staging 57 KB (the bulk stores of two tiles may still be draining)
 // Every MMA takes A from TMEM; shared memory only serves the 3.5 KB B operand (64 B/clk).
 //
 // Warp roles (224 threads): warps 0-3 epilogue (TMEM -> scale -> phase-interleaved staging -> 1-D bulk stores
@@ -44,7 +44,8 @@ constexpr int U_TM_D1 = 128, U_TM_WHI = 240, U_TM_WLO = 376;
 
 constexpr int U_SM_X = 0;                                     // [buf 2][hi/lo 2][U_XT] fp16
 constexpr int U_SM_STAGE = U_SM_X + ((2 * 2 * U_XT * 2 + 127) / 128) * 128;
-constexpr int U_SM_SCALE = U_SM_STAGE + 2 * U_FB * U_PITCH * 4;   // x inverse scales [4], filter inverse scales [16]
+constexpr int U_NSTAGE = 3;               // output staging buffers: the bulk stores of two tiles may still be draining
+constexpr int U_SM_SCALE = U_SM_STAGE + U_NSTAGE * U_FB * U_PITCH * 4;   // x inverse scales [4], filter inverse scales [16]
 constexpr int U_SM_BAR = U_SM_SCALE + 128;
 constexpr int U_SM_TOTAL = U_SM_BAR + 128;
 static_assert(U_FB * U_WPITCH * 4 <= U_FB * U_PITCH * 4, "setup scratch must fit in one staging buffer");
@@ -176,23 +177,30 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
 
   if (warp == 5) {
     // ---------------- producer: waveform tile -> max -> scale -> fp16 hi / lo in shared memory ---------------
+    // The loads of tile it+1 are issued before tile it is converted, so their L2/DRAM latency overlaps the
+    // conversion and the wait for the buffer instead of sitting in front of every tile.
     constexpr int NV = (U_XT + 31) / 32;
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int buf = (int)(it & 1);
-      const uint32_t par = (uint32_t)((it >> 1) & 1);
+    float v[NV], vn[NV];
+    auto load_tile = [&](float (&dst)[NV], int64_t it) {
       const int64_t tile = slot + it * per_blk;
       const int64_t b = tile / a.tiles_per_row;
       const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
       const float* xr = a.x + b * a.xsb;
-      float v[NV];
-      float mx = 0.f;
 #pragma unroll
       for (int r = 0; r < NV; ++r) {
         const int i = lane + 32 * r;
         const int64_t t = t0 - H + i;
-        v[r] = (i < U_XT && t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
-        mx = fmaxf(mx, fabsf(v[r]));
+        dst[r] = (i < U_XT && t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
       }
+    };
+    if (my_tiles > 0) load_tile(v, 0);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int buf = (int)(it & 1);
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      if (it + 1 < my_tiles) load_tile(vn, it + 1);
+      float mx = 0.f;
+#pragma unroll
+      for (int r = 0; r < NV; ++r) mx = fmaxf(mx, fabsf(v[r]));
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       const int se = u_scale_exp(mx);
@@ -214,6 +222,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       tc::fence_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_full[buf]);
+#pragma unroll
+      for (int r = 0; r < NV; ++r) v[r] = vn[r];
     }
   } else if (warp == 4 || warp == 6) {
     // ---------------- MMA issuers: warp 4 takes the even tiles (accumulator 0), warp 6 the odd ones ----------
@@ -260,27 +270,28 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       const int64_t tile = slot + it * per_blk;
       const int64_t b = tile / a.tiles_per_row;
       const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
-      uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage) + buf * (U_FB * U_PITCH * 4);
+      uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage) + (int)(it % U_NSTAGE) * (U_FB * U_PITCH * 4);
       uint8_t* srow = sbuf + cl * PITCHB + r * ESZ;
-      if (lane < 4) tc::bulk_wait_read<1>();   // the stores that read this staging buffer two tiles ago are done
+      if (lane < 4) tc::bulk_wait_read<U_NSTAGE - 1>();   // the stores that read this staging buffer U_NSTAGE tiles ago are done
       tc::named_bar_sync(1, 128);
       ok = ok && tc::mbar_wait(&acc_full[buf], par);
       tc::fence_after_sync();
       const float sc = xinv[it & 3] * wi;      // read before acc_empty is released (the slot is reused 4 tiles later)
       const uint32_t d = tmem + lane_base + (uint32_t)(buf * U_TM_D1);
 #pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {         // 4 x 32 columns; the last 16 of 128 are not part of the accumulator
-        uint32_t v[32];
-        tc::tmem_ld32(d + 32 * ch, v);
+      for (int c2 = 0; c2 < 2; ++c2) {         // 2 x 64 columns, both loads in flight; the last 16 of 128 are not part of the accumulator
+        uint32_t v[64];
+        tc::tmem_ld32(d + 64 * c2, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tc::tmem_ld32(d + 64 * c2 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          if (32 * ch + jj < U_NJ) {
+        for (int jj = 0; jj < 64; ++jj)
+          if (64 * c2 + jj < U_NJ) {
             const float yv = __uint_as_float(v[jj]) * sc;
             if constexpr (OB)
-              *reinterpret_cast<__nv_bfloat16*>(srow + 8 * (32 * ch + jj) * ESZ) = __float2bfloat16_rn(yv);
+              *reinterpret_cast<__nv_bfloat16*>(srow + 8 * (64 * c2 + jj) * ESZ) = __float2bfloat16_rn(yv);
             else
-              *reinterpret_cast<float*>(srow + 8 * (32 * ch + jj) * ESZ) = yv;
+              *reinterpret_cast<float*>(srow + 8 * (64 * c2 + jj) * ESZ) = yv;
           }
       }
       tc::fence_before_sync();

@@ -9,7 +9,7 @@ for rep in reps:
     hdr, units = rows[0], rows[1]
     g = lambda r, k: float(r[hdr.index(k)].replace(",", ""))
     for r in rows[2:]:
-        name = r[hdr.index("Kernel Name")].split("(")[0]
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").split("<")[0].strip()
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         rd = g(r, "dram__bytes_read.sum") * scale[units[hdr.index("dram__bytes_read.sum")]]
         wr = g(r, "dram__bytes_write.sum") * scale[units[hdr.index("dram__bytes_write.sum")]]
