@@ -1,7 +1,9 @@
 // C ABI of libsinc_b200.so: argument validation, engine selection, launch accounting.
 // Declarations and the reference code each entry point replaces: include/sinc_b200.h.
 #include <atomic>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "sinc_internal.h"
 
@@ -17,6 +19,21 @@ constexpr bool kAutoPrefersTcBwdFilter = true;  // parity-green on B200 (r01h)
 constexpr bool kAutoPrefersTcBwdInput = true;   // parity-green on B200 (r01j)
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;  // (kernel, device) -> bytes already granted
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(kernel, dev);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[key] = bytes;
+  return e;
+}
 
 int get_device_info(DeviceInfo* out) {
   static std::mutex mu;

@@ -679,11 +679,11 @@ cudaError_t launch_fwd_fma(const Bank& bank, const float* x, int64_t x_stride_b,
   dim3 grid(gx, cblocks, 1);
   cudaError_t e;
   if (y_dtype == SINC_DTYPE_BF16) {
-    e = cudaFuncSetAttribute(fwd_fma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(fwd_fma_kernel<true>), (int)smem);
     if (e != cudaSuccess) return e;
     fwd_fma_kernel<true><<<grid, FW_THREADS, smem, st>>>(a);
   } else {
-    e = cudaFuncSetAttribute(fwd_fma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(fwd_fma_kernel<false>), (int)smem);
     if (e != cudaSuccess) return e;
     fwd_fma_kernel<false><<<grid, FW_THREADS, smem, st>>>(a);
   }
@@ -707,9 +707,9 @@ cudaError_t launch_bwd_input_fma(const Bank& bank, const void* gy, int gy_dtype,
   const int grid = (int)(a.ntiles < di.sm_count ? a.ntiles : di.sm_count);
   cudaError_t e;
   if (gy_dtype == SINC_DTYPE_BF16)
-    e = cudaFuncSetAttribute(bwd_input_fma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(bwd_input_fma_kernel<true>), (int)smem);
   else
-    e = cudaFuncSetAttribute(bwd_input_fma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(bwd_input_fma_kernel<false>), (int)smem);
   if (e != cudaSuccess) return e;
   for (int cb = 0; cb < bank.C; cb += kChanBlock) {
     a.c_begin = cb;
@@ -755,11 +755,11 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
   dim3 grid(gx, cblocks, kblocks);
   cudaError_t e;
   if (gy_dtype == SINC_DTYPE_BF16) {
-    e = cudaFuncSetAttribute(bwd_filter_fma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(bwd_filter_fma_kernel<true>), (int)smem);
     if (e != cudaSuccess) return e;
     bwd_filter_fma_kernel<true><<<grid, BF_THREADS, smem, st>>>(a);
   } else {
-    e = cudaFuncSetAttribute(bwd_filter_fma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(bwd_filter_fma_kernel<false>), (int)smem);
     if (e != cudaSuccess) return e;
     bwd_filter_fma_kernel<false><<<grid, BF_THREADS, smem, st>>>(a);
   }
@@ -773,7 +773,7 @@ cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slot
   const size_t smem = (size_t)((2 + FN_SPLIT) * bank.K + 32) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e =
-        cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ensure_dynamic_smem(reinterpret_cast<const void*>(finalize_kernel), (int)smem);
     if (e != cudaSuccess) return e;
   }
   finalize_kernel<<<bank.C, FN_THREADS, smem, st>>>(bank, ws_partials, slots, Cpad, Kpad, layout, grad_low, grad_band,

@@ -44,6 +44,8 @@ struct DeviceInfo {
 int get_device_info(DeviceInfo* out);
 
 void count_launch(int n = 1);
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
 
 // ---- tiling constants shared between workspace sizing and the kernels -------------------------
 constexpr int kChanBlock = 64;    // channels handled per CTA (filters kept in shared memory)

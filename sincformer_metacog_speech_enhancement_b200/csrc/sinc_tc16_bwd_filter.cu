@@ -507,7 +507,7 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = F2_SM_TOTAL + 1024;
   auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_filter_tc16_kernel<true> : bwd_filter_tc16_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, F2_THREADS, smem, st>>>(a);
   count_launch();

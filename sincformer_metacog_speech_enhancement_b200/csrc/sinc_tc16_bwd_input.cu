@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
   float* carry = reinterpret_cast<float*>(smem + H2_SM_CARRY);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + H2_SM_BAR);
   uint64_t* b_full = bars;         // [4]  producers (4 warps) -> issuers
-  uint64_t* b_empty = bars + 4;    // [4]  issuers (2 commits) -> producers
+  uint64_t* b_empty = bars + 4;    // [4]  issuer (1 commit per stage) -> producers
   uint64_t* d_full = bars + 8;     // [2 buffers][2 column halves]  issuer -> epilogue
   uint64_t* d_empty = bars + 12;   // [2][2]  epilogue (4 warps) -> issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&b_full[i], 4);
-      tc::mbar_init(&b_empty[i], 2);
+      tc::mbar_init(&b_empty[i], 1);
       tc::mbar_init(&d_full[i], 1);
       tc::mbar_init(&d_empty[i], 4);
     }
@@ -274,8 +274,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
       // ------------- MMA issuers: warp 12 positions 0..63 of the stage, warp 13 positions 64..127 ----------------
       // All lanes of an issuer warp run the loop (warp-uniform operands stay in uniform registers); only the
       // elected lane issues tcgen05 instructions.
-      if (warp < 14) {
-        const int hf = tc::uniform(warp - 12);
+      // ONE issuer (warp 12) does the two 64-column halves of a stage one after the other and hands each to its
+      // epilogue warps as soon as it is complete: the epilogue of half 0 (TMEM loads, shared-memory stores) then
+      // overlaps the MMAs of half 1 instead of all eight epilogue warps hitting the LSU in the same phase.
+      if (warp == 12) {
         const int ncbu = tc::uniform(ncb);
         const int nstu = tc::uniform(nst);
         const int stg0 = tc::uniform((int)(stage & 0x3fffffff));  // only bits 0..1 of the stage counter matter below
@@ -286,30 +288,33 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         for (int i = 0; i < nstu; ++i) {
           const int sg = stg0 + i;
           const int slot = sg & 3, buf = sg & 1;
-          ok = ok && tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1));
           ok = ok && tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 2) & 1));
-          tc::fence_after_sync();
-          const uint32_t d = tm + 128 * buf + 64 * hf;
-          const uint32_t sbase = ring0 + slot * H2_SLOT + hf * 64 * 16;
-          if (tc::elect_one()) {
-            uint32_t acc = 0;
-            for (int e = 0; e < 2; ++e) {
-              uint32_t ah = tm + 256 + 32 * e;
-              uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
-              for (int cb = 0; cb < ncbu; ++cb) {
-                const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
-                tc::mma_f16_ts(d, ah, dh, idesc, acc);
-                if constexpr (!GB) tc::mma_f16_ts(d, ah, dm, idesc, 1);  // bf16 grad_y has no mid planes
-                tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
-                acc = 1;
-                ah += 8;
-                bh += 2 * H2_PLANE;
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            ok = ok && tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1));
+            tc::fence_after_sync();
+            const uint32_t d = tm + 128 * buf + 64 * hf;
+            const uint32_t sbase = ring0 + slot * H2_SLOT + hf * 64 * 16;
+            if (tc::elect_one()) {
+              uint32_t acc = 0;
+              for (int e = 0; e < 2; ++e) {
+                uint32_t ah = tm + 256 + 32 * e;
+                uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
+                for (int cb = 0; cb < ncbu; ++cb) {
+                  const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
+                  tc::mma_f16_ts(d, ah, dh, idesc, acc);
+                  if constexpr (!GB) tc::mma_f16_ts(d, ah, dm, idesc, 1);  // bf16 grad_y has no mid planes
+                  tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
+                  acc = 1;
+                  ah += 8;
+                  bh += 2 * H2_PLANE;
+                }
               }
+              if (hf == 1) tc::mma_commit(&b_empty[slot]);
+              tc::mma_commit(&d_full[2 * buf + hf]);
             }
-            tc::mma_commit(&b_empty[slot]);
-            tc::mma_commit(&d_full[2 * buf + hf]);
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
       __syncwarp();
@@ -423,7 +428,7 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   const int grid = (int)(a.nblocks < di.sm_count ? a.nblocks : di.sm_count);
   const size_t smem = H2_SM_TOTAL + 1024;
   auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_input_tc16_kernel<true> : bwd_input_tc16_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, H2_THREADS, smem, st>>>(a);
   count_launch();

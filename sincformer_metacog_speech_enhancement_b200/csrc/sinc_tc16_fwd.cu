@@ -345,7 +345,7 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = U_SM_TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
   auto kern = y_dtype == SINC_DTYPE_BF16 ? fwd_tc16_kernel<true> : fwd_tc16_kernel<false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, U_THREADS, smem, st>>>(a);
   count_launch();

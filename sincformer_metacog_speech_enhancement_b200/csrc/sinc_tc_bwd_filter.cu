@@ -323,7 +323,7 @@ cudaError_t launch_bwd_filter_tc(const Bank& bank, const float* x, int64_t x_str
   if (per_blk > kMaxPartialSlots) per_blk = kMaxPartialSlots;
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = GF_SM_TOTAL + 1024;
-  cudaError_t e = cudaFuncSetAttribute(bwd_filter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(bwd_filter_tc_kernel), (int)smem);
   if (e != cudaSuccess) return e;
   bwd_filter_tc_kernel<<<grid, GF_THREADS, smem, st>>>(a);
   count_launch();

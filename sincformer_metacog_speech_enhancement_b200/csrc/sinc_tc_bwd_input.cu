@@ -298,7 +298,7 @@ cudaError_t launch_bwd_input_tc(const Bank& bank, const void* gy, float* gx, int
   if (!a.status) return cudaErrorInvalidSymbol;
   const int grid = (int)(a.nblocks < di.sm_count ? a.nblocks : di.sm_count);
   const size_t smem = GI_SM_TOTAL + 1024;
-  cudaError_t e = cudaFuncSetAttribute(bwd_input_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(bwd_input_tc_kernel), (int)smem);
   if (e != cudaSuccess) return e;
   bwd_input_tc_kernel<<<grid, GI_THREADS, smem, st>>>(a);
   count_launch();

@@ -281,7 +281,7 @@ cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, 
   if (per_blk > a.ntiles) per_blk = a.ntiles;
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = TF_SM_TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-  cudaError_t e = cudaFuncSetAttribute(fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(fwd_tc_kernel), (int)smem);
   if (e != cudaSuccess) return e;
   fwd_tc_kernel<<<grid, TF_THREADS, smem, st>>>(a);
   count_launch();

@@ -124,7 +124,7 @@ extern "C" int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int
   a.status = status;
   const size_t smem = ((a_from_tmem ? 0 : bytesA) + 1023) / 1024 * 1024 + (bytesB + 1023) / 1024 * 1024 + 1024;
   if (smem > (size_t)di.max_smem_optin) return SINC_E_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_probe_kernel), (int)smem);
   if (e != cudaSuccess) return (int)e;
   tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a);
   count_launch();

@@ -114,11 +114,10 @@ class SincConvFunction(torch.autograd.Function):
             raise RuntimeError("SincConv1d: empty input")
         y = torch.empty((B, C, T), dtype=out_dtype, device=dev)
         fb = _bank(low, band, win, nn_, sample_rate, min_low_hz, min_band_hz)
-        ws, ws_bytes = _workspace(B, T, C, K, dev)
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             rc = lib.sinc_forward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(y),
-                                  _dtype_code(out_dtype), B, T, _ptr(ws), ws_bytes, ctypes.c_void_p(stream))
+                                  _dtype_code(out_dtype), B, T, None, 0, ctypes.c_void_p(stream))  # no scratch needed
         _lib.check(rc, "sinc_forward")
         ctx.save_for_backward(xd, low, band, win, nn_)
         ctx.attrs = (float(sample_rate), float(min_low_hz), float(min_band_hz))
