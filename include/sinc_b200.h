@@ -37,8 +37,9 @@ extern "C" {
 #define SINC_DTYPE_BF16 1
 
 /* kernel-family selector for sinc_set_engine(): 0 = pick the fastest supported for the shape
- * (default), 1 = FP32 FMA kernels only, 2 = tcgen05 tensor-core kernels only (error if the shape is
- * not supported).  Every engine is hand-written sm_100a CUDA; there is no CPU path. */
+ * (default), 1 = FP32 FMA kernels only, 2 = tcgen05 tensor-core kernels only (16-bit split operands where a
+ * kernel for the shape exists, else 3xTF32; error if neither supports the shape), 3 = tcgen05 with the
+ * 3xTF32 split in every pass.  Every engine is hand-written sm_100a CUDA; there is no CPU path. */
 #define SINC_ENGINE_AUTO 0
 #define SINC_ENGINE_FMA 1
 #define SINC_ENGINE_TC 2
@@ -112,6 +113,33 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
                   int32_t gy_dtype, float* grad_x, float* grad_low, float* grad_band,
                   float* grad_filters, int64_t B, int64_t T, void* workspace,
                   size_t workspace_bytes, void* stream);
+
+/* ---- next row N1: the GroupNorm(8, C) + GELU that follows the layer -----------------
+ * Replaces agents/perception.py:233-234 (the GroupNorm module `sinc_norm` = nn.GroupNorm(8, C) of :157 applied to
+ * the layer output, then F.gelu) with streaming kernels that touch the (B,C,T) activation as few times as possible.  fp32, T % 4 == 0,
+ * 16-byte aligned tensors.
+ *
+ * sinc_forward_gn: sinc_forward (fp32 y) that also emits, from the convolution epilogue, the partial sums the
+ *   GroupNorm statistics need: gn_partial is float2 [B][C/8][sinc_forward_gn_partials(T)] = (sum y, sum y^2) per
+ *   utterance, group of 8 filters and output tile.  SINC_E_ENGINE if the 16-bit tensor-core forward cannot take the
+ *   shape (C % 8 != 0, K > 265, T % 4 != 0) -- then use sinc_forward + sinc_gn_stats.
+ * sinc_gn_stats: one read pass over y -> float2 partial [B*C][sinc_gn_chunks(T)].
+ * sinc_gn_gelu_forward: z = gelu(gamma_c * (y - mean) * rstd + beta_c); `partial` holds, per group, rows_per_group
+ *   rows of np pairs (rows_per_group = C/G, np = sinc_gn_chunks(T) after sinc_gn_stats; rows_per_group = 1,
+ *   np = sinc_forward_gn_partials(T) after sinc_forward_gn); stats (float2 [B][G] = mean, rstd) is an output.
+ * sinc_gn_gelu_backward: dy (and dgamma, dbeta (C) unless both NULL) from dz, y and the saved stats; `partial` is
+ *   float2 scratch [B*C][sinc_gn_chunks(T)]. */
+int64_t sinc_forward_gn_partials(int64_t T);
+int sinc_forward_gn(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, float* y, int64_t B, int64_t T,
+                    float* gn_partial, void* stream);
+int sinc_gn_chunks(int64_t T);
+int sinc_gn_stats(const float* y, int64_t B, int64_t T, int32_t C, float* partial, void* stream);
+int sinc_gn_gelu_forward(const float* y, const float* partial, int32_t np, int32_t rows_per_group, const float* gamma,
+                         const float* beta, float* z, float* stats, int64_t B, int64_t T, int32_t C, int32_t G, float eps,
+                         void* stream);
+int sinc_gn_gelu_backward(const float* dz, const float* y, const float* stats, const float* gamma, const float* beta,
+                          float* dy, float* dgamma, float* dbeta, float* partial, int64_t B, int64_t T, int32_t C,
+                          int32_t G, void* stream);
 
 /* Diagnostic: *status_host = 1 if any tcgen05 kernel of this process gave up waiting on one of its internal
  * barriers (a protocol bug; results are then invalid).  Synchronises the device. */

@@ -2,6 +2,7 @@
 (forward + backward) backed by hand-written sm_100a CUDA kernels behind a C ABI."""
 from .sinc import SincConv1d, SincConvFunction, install_into_reference
 from .distributed import allreduce_filter_grads, shard_rows
+from .frontend import FusedGroupNormGELU, SincFrontEnd
 from . import _lib
 
 
@@ -17,4 +18,4 @@ def kernel_launch_count() -> int:
 
 
 __all__ = ["SincConv1d", "SincConvFunction", "install_into_reference", "allreduce_filter_grads",
-           "shard_rows", "set_engine", "kernel_launch_count"]
+           "shard_rows", "set_engine", "kernel_launch_count", "FusedGroupNormGELU", "SincFrontEnd"]

@@ -20,6 +20,8 @@ ABI_SYMBOLS = (
     "sinc_abi_version", "sinc_strerror", "sinc_kernel_launch_count", "sinc_set_engine",
     "sinc_get_engine", "sinc_last_engine_mask", "sinc_workspace_bytes", "sinc_synthesize",
     "sinc_forward", "sinc_backward", "sinc_tc_probe", "sinc_tc_status",
+    "sinc_forward_gn", "sinc_forward_gn_partials", "sinc_gn_chunks", "sinc_gn_stats", "sinc_gn_gelu_forward",
+    "sinc_gn_gelu_backward",
 )
 
 
@@ -67,6 +69,22 @@ def _declare(lib):
     lib.sinc_backward.argtypes = [c.POINTER(FilterBank), c.c_void_p, c.c_int64, c.c_void_p, c.c_int32,
                                   c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
                                   c.c_int64, c.c_int64, c.c_void_p, c.c_size_t, c.c_void_p]
+    lib.sinc_forward_gn_partials.restype = c.c_int64
+    lib.sinc_forward_gn_partials.argtypes = [c.c_int64]
+    lib.sinc_forward_gn.restype = c.c_int
+    lib.sinc_forward_gn.argtypes = [c.POINTER(FilterBank), c.c_void_p, c.c_int64, c.c_void_p, c.c_int64, c.c_int64,
+                                    c.c_void_p, c.c_void_p]
+    lib.sinc_gn_chunks.restype = c.c_int
+    lib.sinc_gn_chunks.argtypes = [c.c_int64]
+    lib.sinc_gn_stats.restype = c.c_int
+    lib.sinc_gn_stats.argtypes = [c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_void_p, c.c_void_p]
+    lib.sinc_gn_gelu_forward.restype = c.c_int
+    lib.sinc_gn_gelu_forward.argtypes = [c.c_void_p, c.c_void_p, c.c_int32, c.c_int32, c.c_void_p, c.c_void_p, c.c_void_p,
+                                         c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_int32, c.c_float, c.c_void_p]
+    lib.sinc_gn_gelu_backward.restype = c.c_int
+    lib.sinc_gn_gelu_backward.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
+                                          c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_int32,
+                                          c.c_void_p]
     lib.sinc_tc_status.restype = c.c_int
     lib.sinc_tc_status.argtypes = [c.POINTER(c.c_int)]
     lib.sinc_tc_probe.restype = c.c_int

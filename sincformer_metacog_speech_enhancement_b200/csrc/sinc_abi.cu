@@ -179,6 +179,28 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   return 0;
 }
 
+int64_t sinc_forward_gn_partials(int64_t T) { return tc16_fwd_tiles_per_row(T); }
+
+int sinc_forward_gn(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, float* y, int64_t B, int64_t T,
+                    float* gn_partial, void* stream) {
+  int r = check_bank(fb);
+  if (r) return r;
+  if (!x || !y || !gn_partial) return SINC_E_NULL;
+  if (B < 1 || T < 1) return SINC_E_SHAPE;
+  if (reinterpret_cast<uintptr_t>(x) % 4 || reinterpret_cast<uintptr_t>(y) % 4 || reinterpret_cast<uintptr_t>(gn_partial) % 8)
+    return SINC_E_ALIGN;
+  DeviceInfo di;
+  if ((r = check_device(&di))) return r;
+  const Bank bank = to_bank(fb);
+  const int engine = g_engine.load();
+  if (engine == SINC_ENGINE_FMA || engine == SINC_ENGINE_TC_TF32) return SINC_E_ENGINE;
+  if (bank.C % 8 != 0 || !tc16_fwd_supported(bank.C, bank.K, T, y, SINC_DTYPE_F32, di)) return SINC_E_ENGINE;
+  cudaError_t e = launch_fwd_tc16(bank, x, x_stride_b, y, SINC_DTYPE_F32, B, T, di, (cudaStream_t)stream, gn_partial);
+  if (e != cudaSuccess) return (int)e;
+  t_last_mask.store((t_last_mask.load() & ~9) | 9);
+  return 0;
+}
+
 int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, const void* grad_y,
                   int32_t gy_dtype, float* grad_x, float* grad_low, float* grad_band, float* grad_filters,
                   int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream) {

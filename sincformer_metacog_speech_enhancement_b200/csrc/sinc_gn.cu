@@ -1,0 +1,295 @@
+// Next row N1: GroupNorm(8, C) + GELU right after the SincConv output, fused.
+//     reference: agents/perception.py:157 (self.sinc_norm = nn.GroupNorm(8, D // 4)), :233-234
+//                x = self.sinc_norm(x); x = F.gelu(x)
+// The (B,C,T) activation is the largest tensor of the whole Perception Agent (256 B per input sample).  Unfused,
+// torch reads / writes it 5 times in forward (GroupNorm statistics, normalise, GELU) and 7 times in backward.
+// Here: the statistics come out of the convolution epilogue (sinc_tc16_fwd.cu, per-tile partial sums) or from one
+// read pass (gn_stats_kernel), one pass applies normalisation + affine + GELU (read y, write z); backward is two
+// passes (partial sums of du and du*yhat per channel chunk; then dy).  All kernels are HBM-bound streaming kernels:
+// 16-byte accesses, grid sized in multiples of the SM count by the caller, fixed-order fp64 reductions of the
+// partial sums (bitwise reproducible).
+//
+// Layout: y, z, dz, dy are (B,C,T) contiguous; a group's C/G channels are contiguous, so a (b,g) slab is one
+// contiguous run of (C/G)*T elements.  Requirements: T % 4 == 0, 16-byte aligned pointers.
+#include <cuda_bf16.h>
+
+#include "sinc_internal.h"
+
+namespace sinc {
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_CHUNK = 16384;  // elements of one channel row per CTA (64 KB): the per-CTA prologue (fp64 reduction of the
+                                 // group's partial sums) is amortised over 16 float4 per thread, 4 in flight
+
+__device__ __forceinline__ float gelu_f(float u) { return 0.5f * u * (1.f + erff(u * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float u) {
+  const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * u * u);
+  return cdf + u * pdf;
+}
+
+// block-wide sum of two doubles (all threads get the result); scratch: 2 * 32 doubles
+__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) {
+    scratch[w] = a;
+    scratch[32 + w] = b;
+  }
+  __syncthreads();
+  a = 0.0;
+  b = 0.0;
+  for (int i = 0; i < nw; ++i) {  // fixed order
+    a += scratch[i];
+    b += scratch[32 + i];
+  }
+}
+
+// ---- K1: per-chunk partial sums of y and y^2 ------------------------------------------------------------------
+// grid = (B*C, chunks_per_row); partial[(b*C + c) * chunks_per_row + chunk] = (sum, sum of squares)
+__global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ y, int64_t T, int chunks_per_row,
+                                                              float2* __restrict__ partial) {
+  __shared__ double scratch[64];
+  const int64_t row = blockIdx.x;
+  const int chunk = blockIdx.y;
+  const int64_t t0 = (int64_t)chunk * GN_CHUNK;
+  const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
+  const float4* p = reinterpret_cast<const float4*>(y + row * T + t0);
+  float s = 0.f, q = 0.f;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+    const float4 v = __ldg(p + i);
+    s += (v.x + v.y) + (v.z + v.w);
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  double ds = s, dq = q;
+  block_sum2(ds, dq, scratch);
+  if (threadIdx.x == 0) partial[row * chunks_per_row + chunk] = make_float2((float)ds, (float)dq);
+}
+
+// mean / rstd of group (b,g) from `np` partial pairs per channel row (fp64, fixed order); every thread gets them
+__device__ __forceinline__ void group_moments(const float2* __restrict__ partial, int64_t first_row, int rows, int np,
+                                              double count, float eps, double* scratch, float& mean, float& rstd) {
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < rows * np; i += blockDim.x) {
+    const float2 v = __ldg(partial + first_row * np + i);
+    s += (double)v.x;
+    q += (double)v.y;
+  }
+  block_sum2(s, q, scratch);
+  const double m = s / count;
+  double var = q / count - m * m;
+  var = var < 0.0 ? 0.0 : var;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ---- K2: z = gelu(gamma_c * (y - mean) * rstd + beta_c) -----------------------------------------------------
+// grid = (B*C, chunks_per_row); also writes stats[(b*G + g)] = (mean, rstd) (first chunk of the group's first channel)
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_gelu_kernel(const float* __restrict__ y, const float2* __restrict__ partial, int np, int rows_per_group,
+                     const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ z, float2* __restrict__ stats, int64_t T, int C,
+                     int G, int chunks_per_row, float eps) {
+  __shared__ double scratch[64];
+  const int64_t row = blockIdx.x;  // b*C + c
+  const int c = (int)(row % C);
+  const int64_t b = row / C;
+  const int cpg = C / G, g = c / cpg;
+  float mean, rstd;
+  // partial sums of group (b,g): rows_per_group rows of np pairs each (cpg rows from gn_stats_kernel, one row from the
+  // convolution epilogue)
+  group_moments(partial, (b * G + g) * (int64_t)rows_per_group, rows_per_group, np, (double)cpg * (double)T, eps, scratch,
+                mean, rstd);
+  const int chunk = blockIdx.y;
+  if (chunk == 0 && c == g * cpg && threadIdx.x == 0) stats[b * G + g] = make_float2(mean, rstd);
+  const float a = __ldg(gamma + c) * rstd, sh = __ldg(beta + c) - mean * a;  // u = a*y + sh
+  const int64_t t0 = (int64_t)chunk * GN_CHUNK;
+  const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
+  const float4* p = reinterpret_cast<const float4*>(y + row * T + t0);
+  float4* o = reinterpret_cast<float4*>(z + row * T + t0);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+    const float4 v = __ldg(p + i);
+    float4 r;
+    r.x = gelu_f(fmaf(a, v.x, sh));
+    r.y = gelu_f(fmaf(a, v.y, sh));
+    r.z = gelu_f(fmaf(a, v.z, sh));
+    r.w = gelu_f(fmaf(a, v.w, sh));
+    o[i] = r;
+  }
+}
+
+// ---- K3: backward partial sums per channel chunk: (sum du*yhat, sum du), du = dz * gelu'(u) ------------------
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_stats_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float2* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ partial, int64_t T,
+                    int C, int G, int chunks_per_row) {
+  __shared__ double scratch[64];
+  const int64_t row = blockIdx.x;
+  const int c = (int)(row % C);
+  const int64_t b = row / C;
+  const int g = c / (C / G);
+  const float2 st = __ldg(stats + b * G + g);
+  const float mean = st.x, rstd = st.y, ga = __ldg(gamma + c), be = __ldg(beta + c);
+  const int chunk = blockIdx.y;
+  const int64_t t0 = (int64_t)chunk * GN_CHUNK;
+  const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
+  const float4* pz = reinterpret_cast<const float4*>(dz + row * T + t0);
+  const float4* py = reinterpret_cast<const float4*>(y + row * T + t0);
+  float s1 = 0.f, s0 = 0.f;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+    const float4 d = __ldg(pz + i), v = __ldg(py + i);
+    const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float yh = (vv[e] - mean) * rstd;
+      const float du = dd[e] * gelu_grad_f(fmaf(ga, yh, be));
+      s1 = fmaf(du, yh, s1);
+      s0 += du;
+    }
+  }
+  double d1 = s1, d0 = s0;
+  block_sum2(d1, d0, scratch);
+  if (threadIdx.x == 0) partial[row * chunks_per_row + chunk] = make_float2((float)d1, (float)d0);
+}
+
+// ---- K4: dy = rstd * (dyhat - m0 - yhat * m1),  dyhat = gamma_c * du, m = group means of dyhat, dyhat*yhat ----
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float2* __restrict__ stats,
+                    const float2* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    float* __restrict__ dy, int64_t T, int C, int G, int chunks_per_row) {
+  __shared__ double scratch[64];
+  const int64_t row = blockIdx.x;
+  const int c = (int)(row % C);
+  const int64_t b = row / C;
+  const int cpg = C / G, g = c / cpg;
+  // group sums: sum_c gamma_c * (channel sums), fp64, fixed order
+  double m1 = 0.0, m0 = 0.0;
+  for (int i = threadIdx.x; i < cpg * chunks_per_row; i += blockDim.x) {
+    const int cc = g * cpg + i / chunks_per_row;
+    const float2 v = __ldg(partial + (b * C + cc) * chunks_per_row + (i % chunks_per_row));
+    const double gm = (double)__ldg(gamma + cc);
+    m1 += gm * (double)v.x;
+    m0 += gm * (double)v.y;
+  }
+  block_sum2(m1, m0, scratch);
+  const double cnt = (double)cpg * (double)T;
+  const float f1 = (float)(m1 / cnt), f0 = (float)(m0 / cnt);
+  const float2 st = __ldg(stats + b * G + g);
+  const float mean = st.x, rstd = st.y, ga = __ldg(gamma + c), be = __ldg(beta + c);
+  const int chunk = blockIdx.y;
+  const int64_t t0 = (int64_t)chunk * GN_CHUNK;
+  const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
+  const float4* pz = reinterpret_cast<const float4*>(dz + row * T + t0);
+  const float4* py = reinterpret_cast<const float4*>(y + row * T + t0);
+  float4* po = reinterpret_cast<float4*>(dy + row * T + t0);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+    const float4 d = __ldg(pz + i), v = __ldg(py + i);
+    const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w};
+    float r[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float yh = (vv[e] - mean) * rstd;
+      const float dyh = ga * dd[e] * gelu_grad_f(fmaf(ga, yh, be));
+      r[e] = rstd * (dyh - f0 - yh * f1);
+    }
+    po[i] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ---- K5: dgamma_c = sum_{b,chunk} partial.x, dbeta_c = sum partial.y  (grid = C) -----------------------------
+__global__ void __launch_bounds__(GN_THREADS)
+gn_param_grad_kernel(const float2* __restrict__ partial, int64_t B, int C, int chunks_per_row, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta) {
+  __shared__ double scratch[64];
+  const int c = blockIdx.x;
+  double s1 = 0.0, s0 = 0.0;
+  const int64_t total = B * chunks_per_row;
+  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int64_t b = i / chunks_per_row;
+    const float2 v = __ldg(partial + (b * C + c) * chunks_per_row + (i % chunks_per_row));
+    s1 += (double)v.x;
+    s0 += (double)v.y;
+  }
+  block_sum2(s1, s0, scratch);
+  if (threadIdx.x == 0) {
+    dgamma[c] = (float)s1;
+    dbeta[c] = (float)s0;
+  }
+}
+
+static int gn_check(int64_t B, int64_t T, int C, int G, const void* a, const void* b2) {
+  if (B < 1 || T < 1 || C < 1 || G < 1 || C % G) return SINC_E_SHAPE;
+  if (T % 4) return SINC_E_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(a) % 16 || reinterpret_cast<uintptr_t>(b2) % 16) return SINC_E_ALIGN;
+  if (B * C > 2147483647LL) return SINC_E_SHAPE;
+  return 0;
+}
+
+}  // namespace sinc
+
+using namespace sinc;
+
+extern "C" {
+
+int sinc_gn_chunks(int64_t T) { return (int)((T + GN_CHUNK - 1) / GN_CHUNK); }
+
+int sinc_gn_stats(const float* y, int64_t B, int64_t T, int32_t C, float* partial, void* stream) {
+  if (!y || !partial) return SINC_E_NULL;
+  int r = gn_check(B, T, C, 1, y, y);
+  if (r) return r;
+  const int cpr = sinc_gn_chunks(T);
+  gn_stats_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, (cudaStream_t)stream>>>(y, T, cpr,
+                                                                                         reinterpret_cast<float2*>(partial));
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int sinc_gn_gelu_forward(const float* y, const float* partial, int32_t np, int32_t rows_per_group, const float* gamma,
+                         const float* beta, float* z, float* stats, int64_t B, int64_t T, int32_t C, int32_t G, float eps,
+                         void* stream) {
+  if (!y || !partial || !gamma || !beta || !z || !stats) return SINC_E_NULL;
+  int r = gn_check(B, T, C, G, y, z);
+  if (r) return r;
+  if (np < 1 || (rows_per_group != 1 && rows_per_group != C / G)) return SINC_E_SHAPE;
+  const int cpr = sinc_gn_chunks(T);
+  gn_apply_gelu_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, (cudaStream_t)stream>>>(
+      y, reinterpret_cast<const float2*>(partial), np, rows_per_group, gamma, beta, z, reinterpret_cast<float2*>(stats), T, C, G,
+      cpr, eps);
+  count_launch();
+  return (int)cudaGetLastError();
+}
+
+int sinc_gn_gelu_backward(const float* dz, const float* y, const float* stats, const float* gamma, const float* beta,
+                          float* dy, float* dgamma, float* dbeta, float* partial, int64_t B, int64_t T, int32_t C,
+                          int32_t G, void* stream) {
+  if (!dz || !y || !stats || !gamma || !beta || !dy || !partial) return SINC_E_NULL;
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return SINC_E_NULL;
+  int r = gn_check(B, T, C, G, dz, y);
+  if (r) return r;
+  if (reinterpret_cast<uintptr_t>(dy) % 16) return SINC_E_ALIGN;
+  const int cpr = sinc_gn_chunks(T);
+  cudaStream_t st = (cudaStream_t)stream;
+  gn_bwd_stats_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, st>>>(dz, y, reinterpret_cast<const float2*>(stats), gamma,
+                                                                             beta, reinterpret_cast<float2*>(partial), T, C, G, cpr);
+  count_launch();
+  gn_bwd_apply_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, st>>>(dz, y, reinterpret_cast<const float2*>(stats),
+                                                                             reinterpret_cast<const float2*>(partial), gamma, beta,
+                                                                             dy, T, C, G, cpr);
+  count_launch();
+  if (dgamma) {
+    gn_param_grad_kernel<<<C, GN_THREADS, 0, st>>>(reinterpret_cast<const float2*>(partial), B, C, cpr, dgamma, dbeta);
+    count_launch();
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -102,7 +102,8 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
                                   const DeviceInfo& di, cudaStream_t st);
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di);
 cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype, int64_t B,
-                            int64_t T, const DeviceInfo& di, cudaStream_t st);
+                            int64_t T, const DeviceInfo& di, cudaStream_t st, float* gn_partial = nullptr);
+int64_t tc16_fwd_tiles_per_row(int64_t T);
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 size_t tc16_bwd_filter_partial_bytes(int C);
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,

@@ -20,9 +20,9 @@
 //     SMEM  2 x (x_hi, x_lo) tiles 9 KB | 3 x output staging 57 KB (the bulk stores of two tiles may still be draining)
 // Every MMA takes A from TMEM; shared memory only serves the 3.5 KB B operand (64 B/clk).
 //
-// Warp roles (224 threads): warps 0-3 epilogue (TMEM -> scale -> phase-interleaved staging -> 1-D bulk stores
-// of 3.5 KB rows), warps 4 and 6 MMA issuers (even / odd tiles, warp-uniform issue loops), warp 5 waveform
-// producer (global -> max -> scale -> fp16 hi/lo -> smem).
+// Warp roles (352 threads): warps 0-7 epilogue (two per TMEM lane quarter, 56 columns each: TMEM -> scale ->
+// phase-interleaved staging -> 1-D bulk stores of 3.5 KB rows), warps 8 and 10 MMA issuers (even / odd tiles,
+// warp-uniform issue loops), warp 9 waveform producer (global -> max -> scale -> fp16 hi/lo -> smem).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -32,7 +32,7 @@
 
 namespace sinc {
 
-constexpr int U_THREADS = 224;
+constexpr int U_THREADS = 352;  // warps 0-7 epilogue (lane quarter = w%4, column half = w/4), 8 and 10 MMA issuers, 9 waveform producer
 constexpr int U_FB = 16;                  // filters per CTA
 constexpr int U_NJ = 112;                 // MMA N: output groups of 8 samples per tile
 constexpr int U_TT = 8 * U_NJ;            // 896 output samples per tile
@@ -46,7 +46,7 @@ constexpr int U_SM_X = 0;                                     // [buf 2][hi/lo 2
 constexpr int U_SM_STAGE = U_SM_X + ((2 * 2 * U_XT * 2 + 127) / 128) * 128;
 constexpr int U_NSTAGE = 3;               // output staging buffers: the bulk stores of two tiles may still be draining
 constexpr int U_SM_SCALE = U_SM_STAGE + U_NSTAGE * U_FB * U_PITCH * 4;   // x inverse scales [4], filter inverse scales [16]
-constexpr int U_SM_BAR = U_SM_SCALE + 128;
+constexpr int U_SM_BAR = U_SM_SCALE + 256;   // scale area: xinv [4], winv [16], GroupNorm warp sums [8][2]
 constexpr int U_SM_TOTAL = U_SM_BAR + 128;
 static_assert(U_FB * U_WPITCH * 4 <= U_FB * U_PITCH * 4, "setup scratch must fit in one staging buffer");
 
@@ -61,6 +61,8 @@ struct FwdTc16Args {
   int64_t tiles_per_row;
   int64_t ntiles;      // B * tiles_per_row (per filter block)
   int* status;
+  float2* gn_partial;  // optional (next row N1): per (utterance, group of 8 filters, tile) sums of y and y^2 for the
+                       // GroupNorm that follows the layer (agents/perception.py:233), [B][C/8][tiles_per_row]
 };
 
 // power-of-two scale that puts `m` (>= 0) into [2^13, 2^14): returns the exponent, clamped so that both the
@@ -84,7 +86,7 @@ __device__ __forceinline__ void u_split_f16(float v, uint16_t& hi, uint16_t& lo)
   lo = __half_as_ushort(l);
 }
 
-template <bool OB>
+template <bool OB, bool GN>
 __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Args a) {
   constexpr int ESZ = OB ? 2 : 4;                 // bytes per output element
   constexpr int PITCHB = U_PITCH * ESZ;           // staging row pitch in bytes (32 resp. 16 mod 128: conflict free)
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   float* stage = reinterpret_cast<float*>(smem + U_SM_STAGE);   // [2][U_FB][U_PITCH]
   float* xinv = reinterpret_cast<float*>(smem + U_SM_SCALE);    // [4]  1 / sx of tile it & 3
   float* winv = xinv + 4;                                       // [16] 1 / sw_c
+  float* gnred = winv + 16;                                     // [8 warps][2] GroupNorm partial sums of a tile
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + U_SM_BAR);
   uint64_t* x_full = bars + 0;     // [2]
   uint64_t* x_empty = bars + 2;    // [2]
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       tc::mbar_init(&x_full[i], 1);
       tc::mbar_init(&x_empty[i], 1);
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&acc_empty[i], 8);
     }
     tc::mbar_init_fence();
   }
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   const int64_t my_tiles = slot < a.ntiles ? (a.ntiles - slot + per_blk - 1) / per_blk : 0;
   bool ok = true;
 
-  if (warp == 5) {
+  if (warp == 9) {
     // ---------------- producer: waveform tile -> max -> scale -> fp16 hi / lo in shared memory ---------------
     // The loads of tile it+1 are issued before tile it is converted, so their L2/DRAM latency overlaps the
     // conversion and the wait for the buffer instead of sitting in front of every tile.
@@ -225,10 +228,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
 #pragma unroll
       for (int r = 0; r < NV; ++r) v[r] = vn[r];
     }
-  } else if (warp == 4 || warp == 6) {
-    // ---------------- MMA issuers: warp 4 takes the even tiles (accumulator 0), warp 6 the odd ones ----------
+  } else if (warp == 8 || warp == 10) {
+    // ---------------- MMA issuers: warp 8 takes the even tiles (accumulator 0), warp 10 the odd ones ---------
     // All lanes run the loop (warp-uniform operands stay in uniform registers); the elected lane issues.
-    const int buf = tc::uniform(warp == 4 ? 0 : 1);
+    const int buf = tc::uniform(warp == 8 ? 0 : 1);
     const int ntl = tc::uniform((int)my_tiles);
     const int nks = tc::uniform(a.ksteps);
     const uint32_t tm = tc::uniform((int)tmem);
@@ -259,10 +262,14 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       }
       __syncwarp();
     }
-  } else if (warp < 4) {
+  } else if (warp < 8) {
     // ---------------- epilogue: TMEM -> scale -> staging -> bulk stores -------------------------------------
-    const int m = tid, cl = m >> 3, r = m & 7;
-    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    // Two warps per TMEM lane quarter, 56 columns each: the per-tile chain (TMEM load, 56 scaled stores) of a
+    // single warp per quarter was longer than the tile's MMAs (ncu r02d: tensor pipe 65 % active, epilogue warps
+    // never waiting on acc_full).
+    const int m = tid & 127, half = tid >> 7, cl = m >> 3, r = m & 7;
+    const int col0 = (U_NJ / 2) * half;
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const float wi = winv[cl];
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int buf = (int)(it & 1);
@@ -271,36 +278,63 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       const int64_t b = tile / a.tiles_per_row;
       const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
       uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage) + (int)(it % U_NSTAGE) * (U_FB * U_PITCH * 4);
-      uint8_t* srow = sbuf + cl * PITCHB + r * ESZ;
-      if (lane < 4) tc::bulk_wait_read<U_NSTAGE - 1>();   // the stores that read this staging buffer U_NSTAGE tiles ago are done
-      tc::named_bar_sync(1, 128);
+      uint8_t* srow = sbuf + cl * PITCHB + (8 * col0 + r) * ESZ;
+      if (warp == 0 && lane < U_FB) tc::bulk_wait_read<U_NSTAGE - 1>();  // stores that read this buffer U_NSTAGE tiles ago
+      tc::named_bar_sync(1, 256);
       ok = ok && tc::mbar_wait(&acc_full[buf], par);
       tc::fence_after_sync();
       const float sc = xinv[it & 3] * wi;      // read before acc_empty is released (the slot is reused 4 tiles later)
-      const uint32_t d = tmem + lane_base + (uint32_t)(buf * U_TM_D1);
-#pragma unroll 1
-      for (int c2 = 0; c2 < 2; ++c2) {         // 2 x 64 columns, both loads in flight; the last 16 of 128 are not part of the accumulator
-        uint32_t v[64];
-        tc::tmem_ld32(d + 64 * c2, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        tc::tmem_ld32(d + 64 * c2 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < 64; ++jj)
-          if (64 * c2 + jj < U_NJ) {
-            const float yv = __uint_as_float(v[jj]) * sc;
-            if constexpr (OB)
-              *reinterpret_cast<__nv_bfloat16*>(srow + 8 * (64 * c2 + jj) * ESZ) = __float2bfloat16_rn(yv);
-            else
-              *reinterpret_cast<float*>(srow + 8 * (64 * c2 + jj) * ESZ) = yv;
-          }
-      }
+      const int64_t nvalid = T - t0 - r;       // column j is a real output iff 8j < nvalid
+      const uint32_t d = tmem + lane_base + (uint32_t)(buf * U_TM_D1) + col0;
+      uint32_t v[64];                          // 56 columns are this warp's; the load granule is 32
+      tc::tmem_ld32(d, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+      tc::tmem_ld32(d + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      tc::tmem_ld_wait();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator may be overwritten
+      float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};  // GroupNorm sums, 4 independent chains
+#pragma unroll
+      for (int jj = 0; jj < U_NJ / 2; ++jj) {
+        const float yv = __uint_as_float(v[jj]) * sc;
+        if constexpr (GN) {
+          const float yg = 8 * (col0 + jj) < nvalid ? yv : 0.f;
+          gs[jj & 3] += yg;
+          gq[jj & 3] = fmaf(yg, yg, gq[jj & 3]);
+        }
+        if constexpr (OB)
+          *reinterpret_cast<__nv_bfloat16*>(srow + 8 * jj * ESZ) = __float2bfloat16_rn(yv);
+        else
+          *reinterpret_cast<float*>(srow + 8 * jj * ESZ) = yv;
+      }
+      if constexpr (GN) {                      // warp = 4 filters x 8 phases x 56 columns; a group of 8 filters = 4 warps
+        float s = (gs[0] + gs[1]) + (gs[2] + gs[3]), q = (gq[0] + gq[1]) + (gq[2] + gq[3]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s += __shfl_xor_sync(0xffffffffu, s, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) {
+          gnred[2 * warp] = s;
+          gnred[2 * warp + 1] = q;
+        }
+      }
       tc::fence_async_smem();
-      tc::named_bar_sync(1, 128);
-      if (lane < 4) {
-        const int row = 4 * warp + lane;
+      tc::named_bar_sync(1, 256);
+      if constexpr (GN) {
+        if ((tid & 63) == 0 && tid < 128) {    // warps 0 and 2: groups 0 and 1 of this CTA's 16 filters
+          const int gl = tid >> 6;
+          if (c0 + 8 * gl < C) {
+            const int64_t g = c0 / 8 + gl;
+            const int w0 = 2 * gl;             // warps w0, w0+1 (columns 0..55) and w0+4, w0+5 (columns 56..111)
+            a.gn_partial[(b * (C / 8) + g) * a.tiles_per_row + t0 / U_TT] =
+                make_float2((gnred[2 * w0] + gnred[2 * w0 + 2]) + (gnred[2 * w0 + 8] + gnred[2 * w0 + 10]),
+                            (gnred[2 * w0 + 1] + gnred[2 * w0 + 3]) + (gnred[2 * w0 + 9] + gnred[2 * w0 + 11]));
+          }
+        }
+      }
+      if (warp == 0 && lane < U_FB) {
+        const int row = lane;
         const int c = c0 + row;
         if (c < C) {
           const int64_t n = (T - t0) < U_TT ? (T - t0) : U_TT;
@@ -310,7 +344,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
         tc::bulk_commit();
       }
     }
-    if (lane < 4) tc::bulk_wait<0>();
+    if (warp == 0 && lane < U_FB) tc::bulk_wait<0>();
   }
   if (!ok && lane == 0) *a.status = 1;
   tc::fence_before_sync();
@@ -324,8 +358,10 @@ bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, con
   return K + 7 <= U_KS && shape_ok && reinterpret_cast<uintptr_t>(y) % 16 == 0 && di.max_smem_optin >= U_SM_TOTAL + 1024;
 }
 
+int64_t tc16_fwd_tiles_per_row(int64_t T) { return ceil_div64(T, U_TT); }
+
 cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype, int64_t B,
-                            int64_t T, const DeviceInfo& di, cudaStream_t st) {
+                            int64_t T, const DeviceInfo& di, cudaStream_t st, float* gn_partial) {
   FwdTc16Args a;
   a.bank = bank;
   a.x = x;
@@ -338,13 +374,16 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
   a.tiles_per_row = ceil_div64(T, U_TT);
   a.ntiles = B * a.tiles_per_row;
   a.status = tc_status_device_ptr();
+  a.gn_partial = reinterpret_cast<float2*>(gn_partial);
   if (!a.status) return cudaErrorInvalidSymbol;
   int64_t per_blk = di.sm_count / a.nblk;
   if (per_blk < 1) per_blk = 1;
   if (per_blk > a.ntiles) per_blk = a.ntiles;
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = U_SM_TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-  auto kern = y_dtype == SINC_DTYPE_BF16 ? fwd_tc16_kernel<true> : fwd_tc16_kernel<false>;
+  auto kern = y_dtype == SINC_DTYPE_BF16 ? fwd_tc16_kernel<true, false>
+                                         : (gn_partial ? fwd_tc16_kernel<false, true> : fwd_tc16_kernel<false, false>);
+  if (gn_partial && y_dtype != SINC_DTYPE_F32) return cudaErrorInvalidValue;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, U_THREADS, smem, st>>>(a);

@@ -76,7 +76,56 @@ def _small(t: torch.Tensor, name: str, device) -> torch.Tensor:
     if t.dtype != torch.float32:
         raise RuntimeError(f"SincConv1d: {name} must be float32 (got {t.dtype}); the B200 path computes "
                            "in fp32 and does not follow .double()/.half() casts of the module")
-    return t.detach().contiguous()
+    t = t.detach()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs ~10 us)."""
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+def _forward_impl(x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype):
+    """Argument checks + the sinc_forward call; returns (y, tensors to save for backward)."""
+    lib = _lib.load()
+    if not x.is_cuda:
+        raise RuntimeError("SincConv1d (B200): input must be a CUDA tensor -- this implementation has no CPU path")
+    if x.dim() != 3 or x.shape[1] != 1:
+        raise RuntimeError(f"SincConv1d expects (batch, 1, samples); got {tuple(x.shape)}")
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"SincConv1d: input must be float32 (got {x.dtype})")
+    dev = x.device
+    low = _small(low_hz_, "low_hz_", dev)
+    band = _small(band_hz_, "band_hz_", dev)
+    win = _small(window, "window", dev)
+    nn_ = _small(n_, "n_", dev)
+    C, K = low.numel(), win.numel()
+    if K % 2 == 0 or nn_.numel() != (K - 1) // 2 or band.numel() != C:
+        raise RuntimeError("SincConv1d: inconsistent low_hz_/band_hz_/window/n_ shapes")
+    xd = x.detach()
+    if xd.stride(2) != 1 and xd.shape[2] > 1:
+        xd = xd.contiguous()
+    B, _, T = xd.shape
+    if B == 0 or T == 0:
+        raise RuntimeError("SincConv1d: empty input")
+    y = torch.empty((B, C, T), dtype=out_dtype, device=dev)
+    fb = _bank(low, band, win, nn_, sample_rate, min_low_hz, min_band_hz)
+    with _on_device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        rc = lib.sinc_forward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(y),
+                              _dtype_code(out_dtype), B, T, None, 0, ctypes.c_void_p(stream))  # no scratch needed
+    _lib.check(rc, "sinc_forward")
+    return y, (xd, low, band, win, nn_)
 
 
 def _workspace(B, T, C, K, device):
@@ -91,34 +140,8 @@ class SincConvFunction(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype, sync=None):
-        lib = _lib.load()
-        if not x.is_cuda:
-            raise RuntimeError("SincConv1d (B200): input must be a CUDA tensor -- this implementation has no CPU path")
-        if x.dim() != 3 or x.shape[1] != 1:
-            raise RuntimeError(f"SincConv1d expects (batch, 1, samples); got {tuple(x.shape)}")
-        if x.dtype != torch.float32:
-            raise RuntimeError(f"SincConv1d: input must be float32 (got {x.dtype})")
-        dev = x.device
-        low = _small(low_hz_, "low_hz_", dev)
-        band = _small(band_hz_, "band_hz_", dev)
-        win = _small(window, "window", dev)
-        nn_ = _small(n_, "n_", dev)
-        C, K = low.numel(), win.numel()
-        if K % 2 == 0 or nn_.numel() != (K - 1) // 2 or band.numel() != C:
-            raise RuntimeError("SincConv1d: inconsistent low_hz_/band_hz_/window/n_ shapes")
-        xd = x.detach()
-        if xd.stride(2) != 1 and xd.shape[2] > 1:
-            xd = xd.contiguous()
-        B, _, T = xd.shape
-        if B == 0 or T == 0:
-            raise RuntimeError("SincConv1d: empty input")
-        y = torch.empty((B, C, T), dtype=out_dtype, device=dev)
-        fb = _bank(low, band, win, nn_, sample_rate, min_low_hz, min_band_hz)
-        with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = lib.sinc_forward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(y),
-                                  _dtype_code(out_dtype), B, T, None, 0, ctypes.c_void_p(stream))  # no scratch needed
-        _lib.check(rc, "sinc_forward")
+        y, (xd, low, band, win, nn_) = _forward_impl(x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz,
+                                                     min_band_hz, out_dtype)
         ctx.save_for_backward(xd, low, band, win, nn_)
         ctx.attrs = (float(sample_rate), float(min_low_hz), float(min_band_hz))
         ctx.expose_grad_filters = getattr(SincConvFunction, "_expose_grad_filters", False)
@@ -152,7 +175,7 @@ class SincConvFunction(torch.autograd.Function):
             xs0 = xd.stride(0) if B > 1 else T
 
             def launch(want_x, want_p):
-                with torch.cuda.device(dev):
+                with _on_device(dev):
                     stream = torch.cuda.current_stream(dev).cuda_stream
                     rc = lib.sinc_backward(ctypes.byref(fb), _ptr(xd), xs0, _ptr(g), _dtype_code(g.dtype),
                                            _ptr(gx if want_x else None), _ptr(gp[0] if want_p else None),
@@ -237,9 +260,15 @@ class SincConv1d(nn.Module):
                                    f"(channels, samples) and needs 1 channel, got {tuple(waveform.shape)}")
             waveform = waveform.unsqueeze(0)
             unbatched = True
-        y = SincConvFunction.apply(waveform, self.low_hz_, self.band_hz_, self.window, self.n_,
-                                   self.sample_rate, self.min_low_hz, self.min_band_hz, self.out_dtype,
-                                   getattr(self, "_grad_sync", None))
+        needs_graph = torch.is_grad_enabled() and (waveform.requires_grad or self.low_hz_.requires_grad
+                                                   or self.band_hz_.requires_grad)
+        if needs_graph or torch.is_autocast_enabled("cuda"):
+            y = SincConvFunction.apply(waveform, self.low_hz_, self.band_hz_, self.window, self.n_,
+                                       self.sample_rate, self.min_low_hz, self.min_band_hz, self.out_dtype,
+                                       getattr(self, "_grad_sync", None))
+        else:  # inference: straight to the C ABI, no autograd node
+            y, _ = _forward_impl(waveform, self.low_hz_, self.band_hz_, self.window, self.n_, self.sample_rate,
+                                 self.min_low_hz, self.min_band_hz, self.out_dtype)
         return y.squeeze(0) if unbatched else y
 
     def enable_grad_sync(self, group=None, average=False):
