@@ -237,6 +237,28 @@ def test_bitwise_reproducible():
         assert torch.equal(a[k], b[k]), k
 
 
+def test_full_size_bitwise_reproducible():
+    """cfg 2 size, three runs: protocol races in the warp-specialised kernels show up as run-to-run differences long
+    before they show up in a tolerance (that is how the grad-filter flush/MMA overlap problem was found)."""
+    import hashlib
+    torch.manual_seed(0)
+    m = sb.SincConv1d(64, 251, sample_rate=16000).to(dev())
+    x = torch.randn(32, 1, 48000, device=dev())
+    g = torch.randn(32, 64, 48000, device=dev())
+    sigs = set()
+    for _ in range(3):
+        xr = x.clone().requires_grad_(True)
+        m.low_hz_.grad = m.band_hz_.grad = None
+        y = m(xr)
+        y.backward(g)
+        torch.cuda.synchronize()
+        h = hashlib.sha1()
+        for t in (y.detach(), xr.grad, m.low_hz_.grad, m.band_hz_.grad):
+            h.update(t.cpu().numpy().tobytes())
+        sigs.add(h.hexdigest())
+    assert len(sigs) == 1
+
+
 def test_under_autocast_stays_fp32():
     orc, dut = make_pair(8, 31, 8000)
     x = torch.randn(2, 1, 300, generator=torch.Generator().manual_seed(1))
