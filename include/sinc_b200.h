@@ -154,6 +154,12 @@ int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int bytesB, un
                   unsigned long long descB, unsigned int idesc, int ksteps, int a_step, int b_step,
                   int a_from_tmem, int a_cols, int N, float* D_out, int* status_out, void* stream);
 
+
+/* Diagnostic: cycles one SM needs for `count` back-to-back tcgen05.mma (kind::f16, M = 128, N as given) issued by one
+ * thread, rotating through `nacc` accumulators, A from TMEM (1) or shared memory (0).  No counterpart in the
+ * reference; used by tools/mma_rate.py to size the kernels' MMA shapes. */
+int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, long long* cycles_out, int* status_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

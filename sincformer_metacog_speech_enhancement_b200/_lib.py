@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "sinc_get_engine", "sinc_last_engine_mask", "sinc_workspace_bytes", "sinc_synthesize",
     "sinc_forward", "sinc_backward", "sinc_tc_probe", "sinc_tc_status",
     "sinc_forward_gn", "sinc_forward_gn_partials", "sinc_gn_chunks", "sinc_gn_stats", "sinc_gn_gelu_forward",
-    "sinc_gn_gelu_backward",
+    "sinc_gn_gelu_backward", "sinc_tc_mma_rate",
 )
 
 
@@ -85,6 +85,8 @@ def _declare(lib):
     lib.sinc_gn_gelu_backward.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p, c.c_void_p,
                                           c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int64, c.c_int32, c.c_int32,
                                           c.c_void_p]
+    lib.sinc_tc_mma_rate.restype = c.c_int
+    lib.sinc_tc_mma_rate.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.sinc_tc_status.restype = c.c_int
     lib.sinc_tc_status.argtypes = [c.POINTER(c.c_int)]
     lib.sinc_tc_probe.restype = c.c_int

@@ -228,19 +228,22 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
 #pragma unroll
       for (int r = 0; r < NV; ++r) v[r] = vn[r];
     }
-  } else if (warp == 8 || warp == 10) {
-    // ---------------- MMA issuers: warp 8 takes the even tiles (accumulator 0), warp 10 the odd ones ---------
+  } else if (warp == 8) {
+    // ---------------- MMA issuer: all tiles, accumulators alternate -----------------------------------------
     // All lanes run the loop (warp-uniform operands stay in uniform registers); the elected lane issues.
-    const int buf = tc::uniform(warp == 8 ? 0 : 1);
+    // (tools/mma_rate.py: an N = 112 TS-form MMA costs 66 cycles whatever the accumulator rotation, so one
+    // in-order stream loses nothing against two issuers and keeps the MMAs of a tile back to back.)
     const int ntl = tc::uniform((int)my_tiles);
     const int nks = tc::uniform(a.ksteps);
     const uint32_t tm = tc::uniform((int)tmem);
     const uint32_t idesc = tc::make_idesc_f16(128, U_NJ, tc::kFmtF16, tc::kFmtF16);
     const uint64_t bdesc = tc::make_smem_desc(16, 128);      // in-place Toeplitz view of the waveform tile
-    const uint32_t d = tm + (uint32_t)(buf * U_TM_D1);
-    const uint32_t xh_addr = tc::uniform((int)tc::smem_addr(xbuf + (2 * buf) * U_XT));
-    for (int it = buf; it < ntl; it += 2) {
+    const uint32_t x0 = tc::uniform((int)tc::smem_addr(xbuf));
+    for (int it = 0; it < ntl; ++it) {
+      const int buf = it & 1;
       const uint32_t par = (uint32_t)((it >> 1) & 1);
+      const uint32_t d = tm + (uint32_t)(buf * U_TM_D1);
+      const uint32_t xh_addr = x0 + (2 * buf) * U_XT * 2;
       ok = ok && tc::mbar_wait(&acc_empty[buf], par ^ 1);
       ok = ok && tc::mbar_wait(&x_full[buf], par);
       tc::fence_after_sync();

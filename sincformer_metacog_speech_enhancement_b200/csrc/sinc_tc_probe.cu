@@ -130,3 +130,93 @@ extern "C" int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int
   count_launch();
   return (int)cudaGetLastError();
 }
+
+// ---- MMA issue-rate probe (diagnostic): cycles per tcgen05.mma kind::f16, M = 128, for a given N, number of
+// accumulators rotated through, and A operand source -- the numbers DESIGN.md quotes for "what an N = 32 MMA costs".
+namespace sinc {
+
+struct RateArgs {
+  int N, nacc, count, a_from_tmem;
+  long long* cycles;  // [1]
+  int* status;
+};
+
+__global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
+  extern __shared__ __align__(1024) uint8_t rsm[];  // B: 256 rows x 32 bytes (zeros), A (SS form): 128 rows x 32 bytes
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 16384 / 4; i += 128) reinterpret_cast<uint32_t*>(rsm)[i] = 0u;
+  if (tid == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+  }
+  if (warp == 0) {
+    tc::tmem_alloc(&slot, 512);
+    tc::tmem_relinquish();
+  }
+  tc::fence_async_smem();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tm = slot;
+  {  // zero the A columns [448, 512) of every lane
+    uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 64; c += 8) tc::tmem_st8(tm + ((uint32_t)(32 * warp) << 16) + 448 + c, z);
+    tc::tmem_st_wait();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  if (warp == 0) {
+    const uint32_t tmu = tc::uniform((int)tm);
+    const int N = tc::uniform(a.N), nacc = tc::uniform(a.nacc), count = tc::uniform(a.count);
+    const uint32_t idesc = tc::make_idesc_f16(128, N, tc::kFmtBF16, tc::kFmtBF16);
+    const uint64_t bd = tc::desc_at(tc::make_smem_desc(16, 128), tc::uniform((int)tc::smem_addr(rsm)));
+    const uint64_t ad = tc::desc_at(tc::make_smem_desc(16, 128), tc::uniform((int)tc::smem_addr(rsm + 8192)));
+    long long t0 = 0;
+    if (tc::elect_one()) {
+      t0 = clock64();
+      int acc = 0;
+      for (int i = 0; i < count; ++i) {
+        const uint32_t d = tmu + (uint32_t)(acc * N);
+        if (a.a_from_tmem)
+          tc::mma_f16_ts(d, tmu + 448 + 8 * (i & 7), bd, idesc, 1);
+        else
+          tc::mma_f16_ss(d, ad, bd, idesc, 1);
+        acc = acc + 1 == nacc ? 0 : acc + 1;
+      }
+      tc::mma_commit(&bar);
+    }
+    __syncwarp();
+    const bool ok = tc::mbar_wait(&bar, 0);
+    if (tc::elect_one()) {
+      a.cycles[0] = clock64() - t0;
+      if (!ok) *a.status = 1;
+    }
+    __syncwarp();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+
+}  // namespace sinc
+
+extern "C" int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, long long* cycles_out, int* status,
+                                void* stream) {
+  using namespace sinc;
+  if (!cycles_out || !status) return SINC_E_NULL;
+  if (N < 16 || N > 256 || (N % 16) || nacc < 1 || nacc * N > 448 || count < 1) return SINC_E_SHAPE;
+  DeviceInfo di;
+  int r = get_device_info(&di);
+  if (r) return r;
+  if (di.cc_major != 10) return SINC_E_DEVICE;
+  RateArgs a{N, nacc, count, a_from_tmem, cycles_out, status};
+  const size_t smem = 16384 + 1024;
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_mma_rate_kernel), (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  tc_mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a);
+  count_launch();
+  return (int)cudaGetLastError();
+}
