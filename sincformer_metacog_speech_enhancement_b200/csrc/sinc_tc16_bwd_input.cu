@@ -37,7 +37,8 @@
 
 namespace sinc {
 
-constexpr int H2_THREADS = 512;  // warps 0-7 epilogue (quarter = w%4, column half = w/4), 8-11 producers, 12-13 issuers, 14-15 idle
+constexpr int H2_THREADS = 512;  // warps 0-7 epilogue (quarter = w%4, column half = w/4), 8-11 producers, 12 MMA issuer,
+                                 // 13-15 combiners (windows + carry -> gx)
 // setmaxnreg re-partitions the registers the CTA was LAUNCHED with (512 threads x 128), not the whole file:
 constexpr int H2_REGS_WORK = 152;  // epilogue and producer warpgroups
 constexpr int H2_REGS_ISSUE = 40;  // issuer warpgroup
@@ -86,7 +87,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
   uint64_t* b_empty = bars + 4;    // [4]  issuer (1 commit per stage) -> producers
   uint64_t* d_full = bars + 8;     // [2 buffers][2 column halves]  issuer -> epilogue
   uint64_t* d_empty = bars + 12;   // [2][2]  epilogue (4 warps) -> issuer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* win_full = bars + 16;  // [2]  epilogue (8 warps) -> combiners: the windows of a stage are written
+  uint64_t* win_empty = bars + 18; // [2]  combiners (3 warps) -> epilogue: the window buffer may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.bank.C, K = a.bank.K, H = (K - 1) / 2;
@@ -101,6 +104,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
       tc::mbar_init(&b_empty[i], 1);
       tc::mbar_init(&d_full[i], 1);
       tc::mbar_init(&d_empty[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&win_full[i], 8);
+      tc::mbar_init(&win_empty[i], 3);
     }
     tc::mbar_init_fence();
   }
@@ -270,13 +277,49 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
   } else if (warp >= 12) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(H2_REGS_ISSUE));
     for_each_run([&](int64_t b, int64_t s_out, int64_t e_out, int64_t c0, int nst, int64_t stage) {
-      (void)b; (void)s_out; (void)e_out; (void)c0;
       // ------------- MMA issuers: warp 12 positions 0..63 of the stage, warp 13 positions 64..127 ----------------
       // All lanes of an issuer warp run the loop (warp-uniform operands stay in uniform registers); only the
       // elected lane issues tcgen05 instructions.
       // ONE issuer (warp 12) does the two 64-column halves of a stage one after the other and hands each to its
       // epilogue warps as soon as it is complete: the epilogue of half 0 (TMEM loads, shared-memory stores) then
       // overlaps the MMAs of half 1 instead of all eight epilogue warps hitting the LSU in the same phase.
+      if (warp >= 13) {
+        // ------------- combiners (warps 13-15): windows of the eight epilogue warps + carry -> gx ------------------
+        // Decoupled from the epilogue warps by mbarriers: those no longer meet at a CTA-wide barrier every stage.
+        // 96 threads own window cells o = ct + 96 r, r = 0..3 (384 cells); carry is double-buffered in shared memory.
+        const int ct = 32 * (warp - 13) + lane;
+        tc::named_bar_sync(3, 96);  // previous run's carry traffic is done
+        for (int o = ct; o < 256; o += 96) carry[o] = 0.f;  // new run: nothing carried (stage 0 reads carry buffer 0)
+        tc::named_bar_sync(3, 96);
+        for (int i = 0; i < nst; ++i) {
+          const int64_t sg = stage + i;
+          const int buf = (int)(sg & 1), cb = i & 1;
+          const int64_t col0 = c0 + (int64_t)H2_NS * i;  // first position of the stage
+          ok = ok && tc::mbar_wait(&win_full[buf], (uint32_t)((sg >> 1) & 1));
+          const float* wbase = outw + buf * (8 * 128);
+          const float* cin = carry + cb * 256;
+          float* cout = carry + (cb ^ 1) * 256;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int o = ct + 96 * r;
+            float acc = o < 256 ? cin[o] : 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {  // warp w's window starts at cell 64*(q_w + hf_w); fixed order
+              const int rel = o - 64 * ((w & 3) + (w >> 2));
+              if (rel >= 0 && rel < 128) acc += wbase[w * 128 + rel];
+            }
+            if (o < H2_NS) {
+              const int64_t t = col0 - H + o;
+              if (t >= s_out && t < e_out) a.gx[b * T + t] = acc;
+            } else {
+              cout[o - H2_NS] = acc;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&win_empty[buf]);
+          tc::named_bar_sync(3, 96);  // the carry written above is read by other combiner threads in the next stage
+        }
+      }
       if (warp == 12) {
         const int ncbu = tc::uniform(ncb);
         const int nstu = tc::uniform(nst);
@@ -333,8 +376,6 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         m0[m] = (2 * m <= lane) ? 1.f : 0.f;
         m1[m] = (2 * m >= lane + 3) ? 1.f : 0.f;
       }
-      tc::named_bar_sync(2, 256);  // previous run's carry traffic is done
-      carry[tid] = 0.f;            // new run: nothing carried (stage 0 reads carry buffer 0)
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
         const int buf = (int)(sg & 1), cb = i & 1;
@@ -370,35 +411,14 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
           b11 = fmaf(w1, m1[m], b11);
         }
         // chunk 0 covers window cells [0,96): a00 | a01 + a10 | a11; chunk 1 the same 32 cells later
+        ok = ok && tc::mbar_wait(&win_empty[buf], (uint32_t)(((sg >> 1) & 1) ^ 1));  // combined two stages ago
         float* win = outw + buf * (8 * 128) + warp * 128;
         win[lane] = a00;
         win[32 + lane] = (a01 + a10) + b00;
         win[64 + lane] = a11 + (b01 + b10);
         win[96 + lane] = b11;
-        // One barrier per stage: windows and carry are double-buffered, so the reads below cannot race with the
-        // next stage's writes (those come after the next barrier, which every thread passes after these reads).
-        tc::named_bar_sync(2, 256);
-        const float* wbase = outw + buf * (8 * 128);
-        const float* cin = carry + cb * 256;
-        float* cout = carry + (cb ^ 1) * 256;
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int o = tid + 256 * r;
-          if (o < H2_WIN) {
-            float acc = o < 256 ? cin[o] : 0.f;
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {  // warp w's window starts at cell 64*(q_w + hf_w); fixed order
-              const int rel = o - 64 * ((w & 3) + (w >> 2));
-              if (rel >= 0 && rel < 128) acc += wbase[w * 128 + rel];
-            }
-            if (o < H2_NS) {
-              const int64_t t = col0 - H + o;
-              if (t >= s_out && t < e_out) a.gx[b * T + t] = acc;
-            } else {
-              cout[o - H2_NS] = acc;
-            }
-          }
-        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&win_full[buf]);
       }
     });
   }
