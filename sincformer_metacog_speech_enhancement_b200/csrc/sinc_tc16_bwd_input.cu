@@ -47,7 +47,8 @@ constexpr int H2_NS = 128;       // D columns (positions) per stage
 constexpr int H2_SLOTS = 4;      // B ring depth
 constexpr int H2_PLANE = (H2_NS + 1) * 16;       // bytes: halo row + 128 rows of 8 filters x bf16
 constexpr int H2_SLOT = 2 * 8 * H2_PLANE;        // hi planes [8], mid planes [8]
-constexpr int H2_WIN = 384;                      // output window of one stage: 128 positions + 2*127 + 1
+constexpr int H2_WIN = 384;                      // output window of one stage: 128 positions + 2*127 + 1 (3 combiner warps x 4 cells)
+static_assert(H2_WIN == 4 * 96, "combiner cell ownership");
 constexpr int H2_SKEW = 1092;                    // floats per epilogue warp: 2 regions of 16 rows x pitch 34 (+1)
 constexpr int H2_SM_G = 0;                                     // B ring; in the prologue: fp32 filters [64][256]
 constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // skew buffers: one per (epilogue warp, 32-column chunk)
@@ -378,8 +379,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
       }
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
-        const int buf = (int)(sg & 1), cb = i & 1;
-        const int64_t col0 = c0 + (int64_t)H2_NS * i;  // first position of the stage
+        const int buf = (int)(sg & 1);
         ok = ok && tc::mbar_wait(&d_full[2 * buf + hf], (uint32_t)((sg >> 1) & 1));
         tc::fence_after_sync();
         uint32_t va[32], vb[32];
