@@ -79,6 +79,11 @@ uint64_t sinc_kernel_launch_count(void);
 /* Select the kernel family for subsequent calls from this process (SINC_ENGINE_*). */
 int sinc_set_engine(int engine);
 int sinc_get_engine(void);
+/* Data-parallel use: the grad-input kernel is persistent (one CTA per SM, all of its shared memory and registers), so a
+ * collective launched next to it cannot start until it ends.  With n > 0 that kernel leaves n SMs free (process-wide,
+ * 0..64, default 0); the host mirror sets it around the grad-input launch when the parameter-gradient all-reduce
+ * is in flight.  No counterpart in the reference (single process). */
+int sinc_set_reserved_sms(int n);
 /* Which engine the last successful sinc_forward / sinc_backward call of this process actually used:
  * bit 0 forward, bit 1 grad-input, bit 2 grad-filter; a set bit means tcgen05, clear means FMA.
  * Bits 3/4/5 (forward / grad-input / grad-filter): the tcgen05 kernel used 16-bit split operands. */

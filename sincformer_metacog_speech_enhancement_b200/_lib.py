@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "sinc_get_engine", "sinc_last_engine_mask", "sinc_workspace_bytes", "sinc_synthesize",
     "sinc_forward", "sinc_backward", "sinc_tc_probe", "sinc_tc_status",
     "sinc_forward_gn", "sinc_forward_gn_partials", "sinc_gn_chunks", "sinc_gn_stats", "sinc_gn_gelu_forward",
-    "sinc_gn_gelu_backward", "sinc_tc_mma_rate",
+    "sinc_gn_gelu_backward", "sinc_tc_mma_rate", "sinc_set_reserved_sms",
 )
 
 
@@ -54,6 +54,8 @@ def _declare(lib):
     lib.sinc_kernel_launch_count.argtypes = []
     lib.sinc_set_engine.restype = c.c_int
     lib.sinc_set_engine.argtypes = [c.c_int]
+    lib.sinc_set_reserved_sms.restype = c.c_int
+    lib.sinc_set_reserved_sms.argtypes = [c.c_int]
     lib.sinc_get_engine.restype = c.c_int
     lib.sinc_get_engine.argtypes = []
     lib.sinc_last_engine_mask.restype = c.c_int

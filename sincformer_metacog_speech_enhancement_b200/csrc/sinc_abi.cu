@@ -13,10 +13,13 @@ static std::atomic<uint64_t> g_launches{0};
 static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
 // last engine mask: process-wide (backward runs on autograd's own thread, so thread-local would hide it)
 static std::atomic<int> t_last_mask{0};
+static std::atomic<int> g_reserved_sms{0};  // SMs the persistent backward kernels leave free (for a concurrent collective)
 // AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
 constexpr bool kAutoPrefersTcForward = true;  // parity-green on B200 (tests/test_gpu_tc.py, r01c)
 constexpr bool kAutoPrefersTcBwdFilter = true;  // parity-green on B200 (r01h)
 constexpr bool kAutoPrefersTcBwdInput = true;   // parity-green on B200 (r01j)
+
+int reserved_sms() { return g_reserved_sms.load(std::memory_order_relaxed); }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
@@ -118,6 +121,11 @@ int sinc_set_engine(int engine) {
   return 0;
 }
 int sinc_get_engine(void) { return g_engine.load(); }
+int sinc_set_reserved_sms(int n) {
+  if (n < 0 || n > 64) return SINC_E_SHAPE;
+  g_reserved_sms.store(n);
+  return 0;
+}
 int sinc_last_engine_mask(void) { return t_last_mask.load(); }
 
 int sinc_tc_status(int* status_host) {

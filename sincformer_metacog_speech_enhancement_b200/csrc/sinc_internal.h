@@ -44,6 +44,7 @@ struct DeviceInfo {
 int get_device_info(DeviceInfo* out);
 
 void count_launch(int n = 1);
+int reserved_sms();  // sinc_set_reserved_sms(): SMs the persistent grad-input kernel leaves free
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch
 cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
 

@@ -445,7 +445,9 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   a.nblocks = B * a.blocks_per_row;
   a.status = tc_status_device_ptr();
   if (!a.status) return cudaErrorInvalidSymbol;
-  const int grid = (int)(a.nblocks < di.sm_count ? a.nblocks : di.sm_count);
+  int sms = di.sm_count - reserved_sms();  // data-parallel: a few SMs stay free for the all-reduce in flight
+  if (sms < 1) sms = 1;
+  const int grid = (int)(a.nblocks < sms ? a.nblocks : sms);
   const size_t smem = H2_SM_TOTAL + 1024;
   auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_input_tc16_kernel<true> : bwd_input_tc16_kernel<false>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);

@@ -23,6 +23,7 @@ import torch.nn as nn
 from . import _lib
 
 _FALLBACK_SAMPLE_RATE = 8000  # reference config.py:17
+_SYNC_RESERVED_SMS = 4        # SMs left to NCCL while the grad-input kernel runs (enable_grad_sync)
 
 
 def _default_sample_rate():
@@ -191,7 +192,12 @@ class SincConvFunction(torch.autograd.Function):
                 launch(False, True)
                 work = torch.distributed.all_reduce(gp, op=torch.distributed.ReduceOp.SUM, group=group, async_op=True)
                 if need_x:
-                    launch(True, False)
+                    # the grad-input kernel is persistent: leave a few SMs for the NCCL kernel that is in flight
+                    lib.sinc_set_reserved_sms(_SYNC_RESERVED_SMS)
+                    try:
+                        launch(True, False)
+                    finally:
+                        lib.sinc_set_reserved_sms(0)
                 work.wait()
                 if average:
                     gp /= torch.distributed.get_world_size(group)
