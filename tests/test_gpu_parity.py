@@ -332,3 +332,38 @@ def test_full_size_properties():
     # a row of the full-size result against the oracle
     orc = O.OracleSincConv1d(C, 251, sample_rate=16000)
     assert max_rel(y[5].detach().cpu(), orc(x1[5:6].cpu()).detach()[0]) <= TOL_Y
+
+
+def test_indexing_beyond_2_31_elements():
+    """cfg 4 on few GPUs: y has more than 2^31 elements (704 x 64 x 48000 = 2.16e9, 8.7 GB).  Rows at the far end must
+    equal the same rows computed alone (forward, grad-input), and the parameter gradients must equal the sum over two
+    halves of the batch."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~30 GB of device memory")
+    B, T, C = 704, 48000, 64
+    m = sb.SincConv1d(C, 251, sample_rate=16000).to(dev())
+    gen = torch.Generator(device=dev()).manual_seed(7)
+    x = torch.randn(B, 1, T, device=dev(), generator=gen)
+    g = torch.randn(B, C, T, device=dev(), generator=gen)
+    xr = x.clone().requires_grad_(True)
+    y = m(xr)
+    assert y.numel() > 2 ** 31
+    y.backward(g)
+    full = (m.low_hz_.grad.clone(), m.band_hz_.grad.clone())
+    rows = [0, B // 2, B - 1]
+    for r in rows:
+        m.low_hz_.grad = m.band_hz_.grad = None
+        x1 = x[r:r + 1].clone().requires_grad_(True)
+        y1 = m(x1)
+        y1.backward(g[r:r + 1])
+        assert torch.equal(y1[0], y[r]), f"forward row {r}"
+        assert max_rel(x1.grad[0], xr.grad[r]) <= 1e-6, f"grad-input row {r}"
+    del y, y1
+    acc = [torch.zeros_like(full[0]), torch.zeros_like(full[1])]
+    for lo, hi in ((0, B // 2), (B // 2, B)):
+        m.low_hz_.grad = m.band_hz_.grad = None
+        m(x[lo:hi]).backward(g[lo:hi])
+        acc[0] += m.low_hz_.grad
+        acc[1] += m.band_hz_.grad
+    assert max_rel(acc[0], full[0]) <= 1e-4 and max_rel(acc[1], full[1]) <= 1e-4
