@@ -199,6 +199,18 @@ __device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, uint32_t
                "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
                : "memory");
 }
+// global -> shared through a 3-D tensor map (box written densely, optionally swizzled; out-of-range elements
+// read as zero), completes on an mbarrier.  `tmap` = address of a __grid_constant__ CUtensorMap kernel parameter.
+__device__ __forceinline__ void tensor_load_3d(uint32_t sdst, const void* tmap, int x, int y, int z, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          sdst),
+      "l"(tmap), "r"(smem_addr(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tensormap_prefetch(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
 // L2 prefetch of a contiguous global range (no destination, no completion tracking): bytes % 16 == 0, 16-byte aligned
 __device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");

@@ -27,8 +27,10 @@
 // halo row of the next), 2 MMA issuer warps (one per 64-column half), double-buffered accumulators in TMEM,
 // 8 epilogue warps.  A CTA owns a contiguous range of 128-sample output blocks and recomputes the 2H-column halo
 // at the start of each run.
+#include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstring>
 #include <type_traits>
 
 #include "sinc_internal.h"
@@ -44,20 +46,23 @@ constexpr int H2_REGS_WORK = 152;  // epilogue and producer warpgroups
 constexpr int H2_REGS_ISSUE = 40;  // issuer warpgroup
 static_assert(3 * 128 * H2_REGS_WORK + 128 * H2_REGS_ISSUE <= H2_THREADS * 128, "setmaxnreg.inc would block forever");
 constexpr int H2_NS = 128;       // D columns (positions) per stage
-constexpr int H2_SLOTS = 4;      // B ring depth
+constexpr int H2_SLOTS = 2;      // B ring depth (load latency is hidden by the staging boxes, not by the ring)
 constexpr int H2_PLANE = (H2_NS + 1) * 16;       // bytes: halo row + 128 rows of 8 filters x bf16
 constexpr int H2_SLOT = 2 * 8 * H2_PLANE;        // hi planes [8], mid planes [8]
 constexpr int H2_WIN = 384;                      // output window of one stage: 128 positions + 2*127 + 1 (3 combiner warps x 4 cells)
 static_assert(H2_WIN == 4 * 96, "combiner cell ownership");
 constexpr int H2_SKEW = 1092;                    // floats per epilogue warp: 2 regions of 16 rows x pitch 34 (+1)
-constexpr int H2_SM_G = 0;                                     // B ring; in the prologue: fp32 filters [64][256]
+constexpr int H2_STG_BOX = 64 * 32 * 4;                        // one TMA box: 64 filter rows x 32 positions, fp32, 128B-swizzled
+constexpr int H2_SM_STG = 0;                                   // staging: [4 producer warps][2 boxes]
+constexpr int H2_SM_G = H2_SM_STG + 4 * 2 * H2_STG_BOX;        // B ring; in the prologue: fp32 filters [64][256]
 constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // skew buffers: one per (epilogue warp, 32-column chunk)
 constexpr int H2_SM_OUT = H2_SM_S + 8 * 2 * H2_SKEW * 4;       // 2 x 8 x window [128] (double-buffered by stage parity)
 constexpr int H2_SM_CARRY = H2_SM_OUT + 2 * 8 * 128 * 4;       // 2 x carry [256]
 constexpr int H2_SM_BAR = H2_SM_CARRY + 2 * 256 * 4;
 constexpr int H2_SM_TOTAL = H2_SM_BAR + 256;
 static_assert(64 * 256 * 4 <= H2_SLOTS * H2_SLOT, "filter staging must fit in the B ring");
-static_assert(H2_SM_S % 16 == 0 && H2_SM_OUT % 16 == 0, "alignment");
+static_assert(H2_SM_S % 16 == 0 && H2_SM_OUT % 16 == 0 && H2_SM_G % 1024 == 0, "alignment");
+static_assert(H2_SM_TOTAL + 1024 <= 227 * 1024, "shared memory budget");
 
 struct BwdInputTc16Args {
   Bank bank;
@@ -77,8 +82,10 @@ __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, u
 }
 
 template <bool GB>
-__global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const BwdInputTc16Args a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
+__global__ void __launch_bounds__(H2_THREADS, 1)
+    bwd_input_tc16_kernel(const BwdInputTc16Args a, const __grid_constant__ CUtensorMap gmap) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_addr(smem_raw) & 1023u)) & 1023u);  // swizzled boxes: 1024-byte aligned
   uint8_t* ring = smem + H2_SM_G;
   float* skew = reinterpret_cast<float*>(smem + H2_SM_S);
   float* outw = reinterpret_cast<float*>(smem + H2_SM_OUT);
@@ -91,6 +98,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
   uint64_t* win_full = bars + 16;  // [2]  epilogue (8 warps) -> combiners: the windows of a stage are written
   uint64_t* win_empty = bars + 18; // [2]  combiners (3 warps) -> epilogue: the window buffer may be rewritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* st_full = bars + 21;   // [4 producer warps][2]  TMA -> the warp that issued it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.bank.C, K = a.bank.K, H = (K - 1) / 2;
@@ -110,6 +118,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
       tc::mbar_init(&win_full[i], 8);
       tc::mbar_init(&win_empty[i], 3);
     }
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&st_full[i], 1);
+    if constexpr (!GB) tc::tensormap_prefetch(&gmap);
     tc::mbar_init_fence();
   }
   if (warp == 12) {
@@ -140,7 +150,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         uint32_t hi[8], mid[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int c = 16 * cg + 2 * j;
+          // fp32 grad_y: plane cq holds its filter pairs rotated by (cq & 3) -- the order in which the
+          // producers read them conflict-free out of the swizzled staging boxes; W' follows the same order
+          const int cq = 2 * cg + (j >> 2);
+          const int c = GB ? 16 * cg + 2 * j : 8 * cq + ((2 * (j & 3) + 2 * (cq & 3)) & 7);
           split_bf16x2(wst[c * 256 + 2 * kp + e], wst[(c + 1) * 256 + 2 * kp + e], hi[j], mid[j]);
         }
         tc::tmem_st8(tmem + lane_base + 256 + 32 * e + 8 * cg, hi);
@@ -179,21 +192,33 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
 
   if (warp >= 8 && warp < 12) {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(H2_REGS_WORK));
+    // ------------- producers: g[:, p] -> bf16 hi/mid -> row (p - col0 + 1) of the slot's planes -------------------
+    // Warp pw owns 32 positions of every stage; lane (fg, pg) converts 4 consecutive positions of the filters
+    // [8fg, 8fg+8) and [32+8fg, 32+8fg+8) -- two 16-byte plane rows per position.  Neighbouring planes are 16 bytes
+    // apart modulo 128 and lane = 4*pg + fg, so every quarter-warp of an STS.128 covers 8 distinct 16-byte bank
+    // groups: conflict-free.
+    // fp32 grad_y arrives through the TMA engine: each warp keeps two 8 KB boxes (64 filters x its 32 positions,
+    // 128-byte swizzle, rows beyond C and positions outside [0,T) zero-filled) in flight and re-issues a box as soon
+    // as it has read it into registers -- global-load latency is off the conversion path and the L1 data pipe moves
+    // 128-byte wavefronts (LDS.128 of the box) instead of one wavefront per 32-byte sector of an LDG.  Lane (fg, pg)
+    // reads row 8cq + ((j + 2fg) & 7), 16-byte chunk pg ^ row: 8 distinct bank groups per quarter-warp.
+    // bf16 grad_y keeps the direct global loads (LDG.64 of 4 positions, next stage in flight during the wait).
+    const int pw = warp - 8;
+    const int fg = lane & 3, pg = lane >> 2;  // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups
+    const int n0 = 32 * pw + 4 * pg;          // first of this thread's four columns within the stage
+    const uint32_t stg0 = tc::smem_addr(smem + H2_SM_STG + pw * 2 * H2_STG_BOX);
+    uint64_t* my_full = st_full + 2 * pw;
+    uint32_t ldq = 0;                                // boxes consumed so far by this warp (box = ldq & 1)
+    const bool keeps_halo = (pw == 3 && pg == 7);    // these lanes convert the last row of every stage
+    uint4 hsave[2], msave[2];                        // ... which is also row 0 (the halo row) of the next stage's slot
+    hsave[0] = hsave[1] = msave[0] = msave[1] = make_uint4(0u, 0u, 0u, 0u);
     for_each_run([&](int64_t b, int64_t s_out, int64_t e_out, int64_t c0, int nst, int64_t stage) {
       (void)s_out; (void)e_out;
-      // ------------- producers: g[:, p] -> bf16 hi/mid -> row (p - col0 + 1) of the slot's planes -----------------
-      // Warp pw owns 32 positions; lane (fg, pg) loads 4 consecutive positions (one LDG.128 per filter) of the
-      // filters [8fg, 8fg+8) and [32+8fg, 32+8fg+8) -- two 16-byte plane rows per position.  Neighbouring planes
-      // are 16 bytes apart modulo 128 and lane = 4*pg + fg, so every quarter-warp of an STS.128 covers 8 distinct
-      // 16-byte bank groups: conflict-free.
-      const int pw = warp - 8;
-      const int fg = lane & 3, pg = lane >> 2;  // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups
-      const int n0 = 32 * pw + 4 * pg;  // first of this thread's four columns within the stage
       using gvec = typename std::conditional<GB, uint2, float4>::type;   // 4 consecutive positions of one filter row
       constexpr int ESZ = GB ? 2 : 4;
       const uint8_t* gb = reinterpret_cast<const uint8_t*>(a.g) + (b * C) * T * ESZ;
       gvec vv[16];
-      auto load_stage = [&](int64_t p) {  // p = position of column n0 (a multiple of 4; T % 4 == 0)
+      auto load_stage = [&](int64_t p) {  // bf16 path.  p = position of column n0 (a multiple of 4; T % 4 == 0)
         const bool in = p >= 0 && p < T;
         const uint8_t* q = gb + ((in ? p : 0) + (int64_t)(8 * fg) * T) * ESZ;  // one running row pointer: no address array
 #pragma unroll
@@ -201,41 +226,78 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
           const int c = 8 * fg + (j & 7) + 32 * (j >> 3);
           if constexpr (GB)
             vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const uint2*>(q)) : make_uint2(0u, 0u);
-          else
-            vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(0.f, 0.f, 0.f, 0.f);
           q += ((j == 7) ? 25 * T : T) * ESZ;
         }
       };
+      auto issue_box = [&](int i, uint32_t q) {  // stage i of this run -> box q & 1 (the whole warp calls; one lane issues)
+        if (tc::elect_one()) {
+          uint64_t* bar = &my_full[q & 1];
+          tc::mbar_expect_tx(bar, H2_STG_BOX);
+          tc::tensor_load_3d(stg0 + (q & 1) * H2_STG_BOX, &gmap, (int)(c0 + (int64_t)H2_NS * i + 32 * pw), 0, (int)b, bar);
+        }
+        __syncwarp();
+      };
+      if constexpr (!GB) {
+        issue_box(0, ldq);
+        if (nst > 1) issue_box(1, ldq + 1);
+      }
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
-        const int slot = (int)(sg & 3);
-        // Stage sg-3 complete => slot (sg+1)&3 (the halo target) is free, and so is slot sg&3 (in-order MMAs).
-        if (sg >= 3) ok = ok && tc::mbar_wait(&b_empty[(sg + 1) & 3], (uint32_t)(((sg - 3) >> 2) & 1));
+        const int slot = (int)(sg & 1);
+        if constexpr (!GB) {
+          ok = ok && tc::mbar_wait(&my_full[ldq & 1], (ldq >> 1) & 1);
+          const uint32_t box = stg0 + (ldq & 1) * H2_STG_BOX;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int cq = fg + 4 * (j >> 3);
+            const int r7 = ((j & 7) + 2 * fg) & 7;
+            const uint32_t addr = box + (8 * cq + r7) * 128 + ((pg ^ r7) << 4);
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(vv[j].x), "=f"(vv[j].y), "=f"(vv[j].z), "=f"(vv[j].w)
+                         : "r"(addr)
+                         : "memory");
+          }
+          __syncwarp();
+          if (i + 2 < nst) issue_box(i + 2, ldq + 2);  // same box: its contents are in registers now
+          ++ldq;
+        } else {
+          if (i == 0) load_stage(c0 + n0);
+        }
+        // slot sg & 1 was last read by the MMAs of stage sg - 2
+        if (sg >= 2) ok = ok && tc::mbar_wait(&b_empty[slot], (uint32_t)(((sg - 2) >> 1) & 1));
         uint8_t* base = ring + slot * H2_SLOT;
         if (i == 0) {
           if (pw == 0) {  // run start: the halo row (position c0 - 1) has no previous stage; lane = filter pair
             const int64_t p = c0 - 1;
             const bool in = p >= 0 && p < T;
+            const int hq = lane >> 2;                                                      // plane
+            const int hc = GB ? 2 * lane : 8 * hq + ((2 * (lane & 3) + 2 * (hq & 3)) & 7);  // first filter of the pair
             uint32_t h, m;
             if constexpr (GB) {
               const uint16_t* g16 = reinterpret_cast<const uint16_t*>(gb);
-              const uint32_t w0 = (in && 2 * lane < C) ? __ldg(g16 + (int64_t)(2 * lane) * T + p) : 0u;
-              const uint32_t w1 = (in && 2 * lane + 1 < C) ? __ldg(g16 + (int64_t)(2 * lane + 1) * T + p) : 0u;
+              const uint32_t w0 = (in && hc < C) ? __ldg(g16 + (int64_t)hc * T + p) : 0u;
+              const uint32_t w1 = (in && hc + 1 < C) ? __ldg(g16 + (int64_t)(hc + 1) * T + p) : 0u;
               h = w0 | (w1 << 16);
               m = 0u;
             } else {
               const float* g32 = reinterpret_cast<const float*>(gb);
-              const float w0 = (in && 2 * lane < C) ? __ldg(g32 + (int64_t)(2 * lane) * T + p) : 0.f;
-              const float w1 = (in && 2 * lane + 1 < C) ? __ldg(g32 + (int64_t)(2 * lane + 1) * T + p) : 0.f;
+              const float w0 = (in && hc < C) ? __ldg(g32 + (int64_t)hc * T + p) : 0.f;
+              const float w1 = (in && hc + 1 < C) ? __ldg(g32 + (int64_t)(hc + 1) * T + p) : 0.f;
               split_bf16x2(w0, w1, h, m);
             }
-            *reinterpret_cast<uint32_t*>(base + (lane >> 2) * H2_PLANE + (lane & 3) * 4) = h;
-            if constexpr (!GB) *reinterpret_cast<uint32_t*>(base + (8 + (lane >> 2)) * H2_PLANE + (lane & 3) * 4) = m;
+            *reinterpret_cast<uint32_t*>(base + hq * H2_PLANE + (lane & 3) * 4) = h;
+            if constexpr (!GB) *reinterpret_cast<uint32_t*>(base + (8 + hq) * H2_PLANE + (lane & 3) * 4) = m;
           }
-          load_stage(c0 + n0);
+        } else if (keeps_halo) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const int cq = fg + 4 * s2;
+            if (cq < 2 * ncb) {
+              *reinterpret_cast<uint4*>(base + cq * H2_PLANE) = hsave[s2];
+              if constexpr (!GB) *reinterpret_cast<uint4*>(base + (8 + cq) * H2_PLANE) = msave[s2];
+            }
+          }
         }
-        // the last row of a stage is also the halo row (row 0) of the next stage's slot
-        uint8_t* dup = (pw == 3 && pg == 7 && i + 1 < nst) ? ring + (int)((sg + 1) & 3) * H2_SLOT : nullptr;
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
           const int cq = fg + 4 * s2;
@@ -262,14 +324,16 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
               uint8_t* dst = base + cq * H2_PLANE + (n0 + o + 1) * 16;
               *reinterpret_cast<uint4*>(dst) = h;
               if constexpr (!GB) *reinterpret_cast<uint4*>(dst + 8 * H2_PLANE) = m;
-              if (o == 3 && dup) {
-                *reinterpret_cast<uint4*>(dup + cq * H2_PLANE) = h;
-                if constexpr (!GB) *reinterpret_cast<uint4*>(dup + (8 + cq) * H2_PLANE) = m;
+              if (o == 3) {
+                hsave[s2] = h;
+                msave[s2] = m;
               }
             }
           }
         }
-        if (i + 1 < nst) load_stage(c0 + (int64_t)H2_NS * (i + 1) + n0);  // in flight during the next wait
+        if constexpr (GB) {
+          if (i + 1 < nst) load_stage(c0 + (int64_t)H2_NS * (i + 1) + n0);  // in flight during the next wait
+        }
         tc::fence_async_smem();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&b_full[slot]);
@@ -331,8 +395,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1) bwd_input_tc16_kernel(const Bwd
         const uint64_t bdesc = tc::make_smem_desc(H2_PLANE, 128);  // K chunk stride = plane, 8-row groups contiguous
         for (int i = 0; i < nstu; ++i) {
           const int sg = stg0 + i;
-          const int slot = sg & 3, buf = sg & 1;
-          ok = ok && tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 2) & 1));
+          const int slot = sg & 1, buf = sg & 1;
+          ok = ok && tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 1) & 1));
 #pragma unroll 1
           for (int hf = 0; hf < 2; ++hf) {
             ok = ok && tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1));
@@ -433,6 +497,36 @@ bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtyp
          reinterpret_cast<uintptr_t>(g) % 16 == 0 && di.max_smem_optin >= H2_SM_TOTAL + 1024;
 }
 
+namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point table: the library does not link libcuda.
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// grad_y [B][C][T] fp32 as a 3-D tensor (T fastest); box = 32 positions x 64 filters of one utterance, 128-byte swizzle
+bool make_grad_map(CUtensorMap* m, const void* g, int64_t B, int C, int64_t T) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)T * 4, (cuuint64_t)T * 4 * (cuuint64_t)C};
+  const cuuint32_t box[3] = {32, 64, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
 cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
                                   const DeviceInfo& di, cudaStream_t st) {
   BwdInputTc16Args a;
@@ -452,7 +546,10 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_input_tc16_kernel<true> : bwd_input_tc16_kernel<false>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, H2_THREADS, smem, st>>>(a);
+  CUtensorMap gmap;
+  memset(&gmap, 0, sizeof(gmap));
+  if (gy_dtype != SINC_DTYPE_BF16 && !make_grad_map(&gmap, gy, B, bank.C, T)) return cudaErrorNotSupported;
+  kern<<<grid, H2_THREADS, smem, st>>>(a, gmap);
   count_launch();
   return cudaGetLastError();
 }
