@@ -150,6 +150,13 @@ int sinc_gn_gelu_backward(const float* dz, const float* y, const float* stats, c
  * barriers (a protocol bug; results are then invalid).  Synchronises the device. */
 int sinc_tc_status(int* status_host);
 
+/* Diagnostic: time stamps of the LAST launch of each 16-bit tcgen05 kernel, taken by CTA 0: out20[6*k + ...] =
+ * {SM cycle counter, nanosecond timer} at kernel entry, after the prologue (filter synthesis, operand set-up) and
+ * at exit, for k = 0 forward, 1 grad-input, 2 grad-filter.  cycles / ns = the SM clock the kernel really ran at.
+ * out20[18] = 1 if that grad-input launch took its filters from the table the grad-filter kernel leaves in the
+ * workspace, 0 if it synthesised them.  Synchronises the device. */
+int sinc_tc_phase_stamps(long long* out20);
+
 /* Diagnostic: run `ksteps` tcgen05.mma (kind::tf32, M = 128) on caller-supplied shared-memory images and
  * raw matrix / instruction descriptors and return the 128 x N accumulator.  Not part of the replacement
  * surface (the reference has no counterpart); it exists so the operand layouts the tensor-core engine

@@ -70,7 +70,8 @@ WorkspaceLayout workspace_layout(int C, int K) {
   if (tc_bytes > wl.partial_bytes) wl.partial_bytes = tc_bytes;
   const size_t tc16_bytes = tc16_bwd_filter_partial_bytes(C);
   if (tc16_bytes > wl.partial_bytes) wl.partial_bytes = tc16_bytes;
-  wl.total_bytes = (wl.partial_bytes + 255) / 256 * 256 + 256;
+  wl.table_offset = (wl.partial_bytes + 255) / 256 * 256;
+  wl.total_bytes = wl.table_offset + kFilterTableBytes + 256;
   return wl;
 }
 
@@ -127,6 +128,11 @@ int sinc_set_reserved_sms(int n) {
   return 0;
 }
 int sinc_last_engine_mask(void) { return t_last_mask.load(); }
+
+int sinc_tc_phase_stamps(long long* out20) {
+  if (!out20) return SINC_E_NULL;
+  return read_tc_phase(out20);
+}
 
 int sinc_tc_status(int* status_host) {
   if (!status_host) return SINC_E_NULL;
@@ -229,22 +235,15 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   cudaError_t e;
   int mask = 0;
   const int engine = g_engine.load();
-  if (grad_x) {
-    const bool tc_ok = tc_bwd_input_supported(bank.C, bank.K, grad_y, gy_dtype, di);
-    const bool tc16_ok = tc16_bwd_input_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
-    const bool want_tc = engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
-                         (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdInput);
-    const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
-    const bool use_tc = want_tc && tc_ok && !use_tc16;
-    if (use_tc16)
-      e = launch_bwd_input_tc16(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
-    else if (use_tc)
-      e = launch_bwd_input_tc(bank, grad_y, grad_x, B, T, di, st);
-    else
-      e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
-    if (e != cudaSuccess) return (int)e;
-    mask |= (use_tc || use_tc16) ? 2 : 0;
-    mask |= use_tc16 ? 16 : 0;
+  // The filter table (sinc_synth.cuh): written by the 16-bit grad-filter kernel, read -- after validation -- by the
+  // 16-bit grad-input kernel.  Parameter gradients therefore go first when both are wanted; a grad-input-only call
+  // finds the table of the preceding parameter-gradient call on the same workspace (data parallel: the all-reduce
+  // of the parameter gradients is in flight in between) or synthesises the filters itself.
+  uint8_t* filter_table = nullptr;
+  {
+    const WorkspaceLayout wl = workspace_layout(bank.C, bank.K);
+    if (workspace && workspace_bytes >= wl.total_bytes)
+      filter_table = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256) + wl.table_offset;
   }
   if (want_params) {
     const WorkspaceLayout wl = workspace_layout(bank.C, bank.K);
@@ -258,7 +257,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
     if (use_tc16)
-      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
+      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table);
     else if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else
@@ -269,6 +268,23 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     if (e != cudaSuccess) return (int)e;
     mask |= (use_tc || use_tc16) ? 4 : 0;
     mask |= use_tc16 ? 32 : 0;
+  }
+  if (grad_x) {
+    const bool tc_ok = tc_bwd_input_supported(bank.C, bank.K, grad_y, gy_dtype, di);
+    const bool tc16_ok = tc16_bwd_input_supported(bank.C, bank.K, T, grad_y, gy_dtype, di);
+    const bool want_tc = engine == SINC_ENGINE_TC || engine == SINC_ENGINE_TC_TF32 ||
+                         (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdInput);
+    const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
+    const bool use_tc = want_tc && tc_ok && !use_tc16;
+    if (use_tc16)
+      e = launch_bwd_input_tc16(bank, grad_y, gy_dtype, grad_x, B, T, di, st, filter_table);
+    else if (use_tc)
+      e = launch_bwd_input_tc(bank, grad_y, grad_x, B, T, di, st);
+    else
+      e = launch_bwd_input_fma(bank, grad_y, gy_dtype, grad_x, B, T, di, st);
+    if (e != cudaSuccess) return (int)e;
+    mask |= (use_tc || use_tc16) ? 2 : 0;
+    mask |= use_tc16 ? 16 : 0;
   }
   t_last_mask.store((t_last_mask.load() & 9) | mask);
   return 0;

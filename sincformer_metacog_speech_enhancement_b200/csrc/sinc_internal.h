@@ -51,6 +51,7 @@ cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
 // ---- tiling constants shared between workspace sizing and the kernels -------------------------
 constexpr int kChanBlock = 64;    // channels handled per CTA (filters kept in shared memory)
 constexpr int kTapBlock = 256;    // taps handled per grad-filter CTA
+constexpr size_t kFilterTableBytes = 4096 + 64 * 256 * 4;  // header + W[64][256] (layout: sinc_synth.cuh)
 constexpr int kMaxPartialSlots = 2 * 160;  // grad-filter partial tiles (2 CTAs/SM, <=160 SMs)
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -62,6 +63,7 @@ struct WorkspaceLayout {
   int Cpad;         // C rounded up to kChanBlock
   int Kpad;         // K rounded up to kTapBlock
   size_t partial_bytes;
+  size_t table_offset;  // filter table (sinc_synth.cuh), from the 256-byte aligned workspace base
   size_t total_bytes;
 };
 WorkspaceLayout workspace_layout(int C, int K);
@@ -86,6 +88,8 @@ bool tc_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const
 cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
                           const DeviceInfo& di, cudaStream_t st);
 int read_tc_status(int* out);
+long long* tc_phase_device_ptr();  // device address of the phase time stamps (see sinc_tc_fwd.cu)
+int read_tc_phase(long long* out20);
 int* tc_status_device_ptr();  // device address of the shared 'barrier wait timed out' flag
 bool tc_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 size_t tc_bwd_filter_partial_bytes(int C);
@@ -100,7 +104,7 @@ cudaError_t launch_bwd_input_tc(const Bank& bank, const void* gy, float* gx, int
 // 16-bit split variants (bf16 hi/mid, three kind::f16 MMAs): sinc_tc16_*.cu
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
-                                  const DeviceInfo& di, cudaStream_t st);
+                                  const DeviceInfo& di, cudaStream_t st, const uint8_t* filter_table);
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di);
 cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype, int64_t B,
                             int64_t T, const DeviceInfo& di, cudaStream_t st, float* gn_partial = nullptr);
@@ -109,6 +113,6 @@ bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dty
 size_t tc16_bwd_filter_partial_bytes(int C);
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st);
+                                   cudaStream_t st, uint8_t* filter_table);
 
 }  // namespace sinc

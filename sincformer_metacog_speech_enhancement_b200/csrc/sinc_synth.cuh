@@ -61,7 +61,7 @@ __device__ __noinline__ void synth_filter_warp(const Bank& bk, int c, int lane, 
   const float fd = (float)(0.5 * (cc.f_hi - cc.f_lo));  // (a-b)/2 = fd * n
   auto left32 = [&](int j) -> float {
     const float nj = bk.n[j];
-    return 2.0f * cosf(fs * nj) * sinf(fd * nj) / (nj * 0.5f + 1e-8f);
+    return __fdividef(2.0f * cosf(fs * nj) * sinf(fd * nj), nj * 0.5f + 1e-8f);  // 2 ulp quotient: inside the 3e-7 target
   };
   constexpr int R = 4;  // taps cached in registers per lane: covers H <= 128 (K <= 257)
   float ul[R], ur[R];
@@ -87,20 +87,83 @@ __device__ __noinline__ void synth_filter_warp(const Bank& bk, int c, int lane, 
   if (lane == 0) sumabs += (double)fabsf(uc);
   const double S = warp_sum(sumabs) + 1e-8;  // :112
   if (S_out) *S_out = S;
+  // one fp64 reciprocal instead of a division per tap (the quotient differs from u / S in the last bit of a double,
+  // far below the fp32 rounding of the result); the prologue of every convolution kernel runs this function
+  const double rS = 1.0 / S;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int j = r * 32 + lane;
     if (j < H) {
-      emit(j, (double)ul[r] / S);
-      emit(K - 1 - j, (double)ur[r] / S);
+      emit(j, (double)ul[r] * rS);
+      emit(K - 1 - j, (double)ur[r] * rS);
     }
   }
   for (int j = R * 32 + lane; j < H; j += 32) {
     const float left = left32(j);
-    emit(j, (double)(left * bk.window[j]) / S);
-    emit(K - 1 - j, (double)(left * bk.window[K - 1 - j]) / S);
+    emit(j, (double)(left * bk.window[j]) * rS);
+    emit(K - 1 - j, (double)(left * bk.window[K - 1 - j]) * rS);
   }
-  if (lane == 0) emit(H, (double)uc / S);
+  if (lane == 0) emit(H, (double)uc * rS);
+}
+
+// ---- filter table in the workspace -----------------------------------------------------------------------------
+// The grad-filter kernel (16-bit tcgen05 engine) has idle warps at its start; they synthesise the filters ONCE and
+// leave them in the workspace, so that the grad-input kernel -- launched later on the same stream -- does not spend
+// its prologue synthesising all 64 filters in every CTA (ncu r04b: 14 % of that kernel).  The table is self-
+// validating, because a workspace is caller memory that may be recycled between calls: a header holds an exact copy
+// of everything the synthesis depends on (C, K, sample rate, minima, low_hz_, band_hz_, window, n_) and a checksum
+// per row; the consumer compares the header with ITS filter bank word by word and re-computes the row checksums
+// while it copies the rows, and synthesises the filters itself on any mismatch.
+constexpr int kTabHdrWords = 8 + 64 + 64 + 256 + 128;       // 520 32-bit words
+constexpr int kTabRowsumOff = 2112;                         // bytes: 64 x uint64 row checksums
+constexpr int kTabDataOff = 4096;                           // bytes: float W[64][256], zero outside [0,C) x [0,K)
+static_assert(kTabDataOff + 64 * 256 * 4 == kFilterTableBytes, "workspace_layout reserves the table");
+
+__device__ __forceinline__ bool tab_shape_ok(const Bank& bk) { return bk.C <= 64 && bk.K <= 256; }
+
+// word i of the header for this filter bank
+__device__ __forceinline__ uint32_t tab_header_word(const Bank& bk, int i) {
+  const int H = (bk.K - 1) / 2;
+  if (i < 8) {
+    if (i == 0) return (uint32_t)bk.C;
+    if (i == 1) return (uint32_t)bk.K;
+    const double d = i < 4 ? bk.sr : i < 6 ? bk.min_low : bk.min_band;
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (i & 1) ? (uint32_t)(u >> 32) : (uint32_t)u;
+  }
+  i -= 8;
+  if (i < 64) return i < bk.C ? __float_as_uint(bk.low_hz[i]) : 0u;
+  i -= 64;
+  if (i < 64) return i < bk.C ? __float_as_uint(bk.band_hz[i]) : 0u;
+  i -= 64;
+  if (i < 256) return i < bk.K ? __float_as_uint(bk.window[i]) : 0u;
+  i -= 256;
+  return i < H ? __float_as_uint(bk.n[i]) : 0u;
+}
+
+__device__ __forceinline__ unsigned long long tab_mix(float w, int k) {
+  return (unsigned long long)__float_as_uint(w) * (unsigned long long)(2 * k + 1);
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Whole-warp call: row c of the table (+ its checksum).
+__device__ __forceinline__ void tab_write_row(const Bank& bk, uint8_t* tab, int c, int lane) {
+  float* row = reinterpret_cast<float*>(tab + kTabDataOff) + c * 256;
+  for (int k = lane; k < 256; k += 32)
+    if (c >= bk.C || k >= bk.K) row[k] = 0.f;
+  unsigned long long sum = 0ull;
+  if (c < bk.C)
+    synth_filter_warp(bk, c, lane, [&](int k, double w) {
+      const float wf = (float)w;
+      row[k] = wf;
+      sum += tab_mix(wf, k);
+    });
+  sum = warp_sum_u64(sum);
+  if (lane == 0) reinterpret_cast<unsigned long long*>(tab + kTabRowsumOff)[c] = sum;
 }
 
 // ---- small PTX helpers used by several kernels -------------------------------------------------

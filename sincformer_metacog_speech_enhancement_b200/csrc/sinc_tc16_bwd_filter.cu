@@ -28,6 +28,7 @@
 #include <cuda_bf16.h>
 
 #include "sinc_internal.h"
+#include "sinc_synth.cuh"
 #include "sinc_tc.cuh"
 
 namespace sinc {
@@ -85,6 +86,9 @@ struct BwdFilterTc16Args {
   int64_t tiles_per_row;
   int64_t ntiles;
   int* status;
+  long long* phase;  // diagnostic time stamps (CTA 0), may be null
+  Bank bank;         // only read when tab != nullptr
+  uint8_t* tab;      // filter table for the grad-input kernel (sinc_synth.cuh), or nullptr
 };
 
 __device__ __forceinline__ void f2_split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& mid) {
@@ -106,6 +110,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   using gvec = typename G::vec;
   constexpr int GPITCH = G::pitch;
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[0] = clock64();
+    a.phase[1] = (long long)tc::global_timer_ns();
+  }
   uint16_t* xs = reinterpret_cast<uint16_t*>(smem + F2_SM_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_SM_BAR);
   uint64_t* a_full = bars;            // [F2_RING]  producers (4 warps of one group) -> issuers
@@ -158,6 +166,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   const int64_t tile_end = a.ntiles * (slot + 1) / per_blk;
   const int64_t my_tiles = tile_end - tile_begin;
   bool ok = true;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[2] = clock64();
+    a.phase[3] = (long long)tc::global_timer_ns();
+  }
 
   if (warp < 8) {
     // ------------- grad_y converters (staged fp32 rows -> bf16 hi/mid -> TMEM ring) --------------------------
@@ -432,6 +444,14 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     }
   } else if (warp >= 12) {
     // ------------- flush warps: accumulator set -> the CTA's partial tile (fixed order, no atomics) ------------
+    // They have nothing to do until the first window is complete: first they leave the synthesised filters in the
+    // workspace for the grad-input kernel that follows on this stream (sinc_synth.cuh, "filter table").
+    if (a.tab) {
+      if (blockIdx.x == 0)
+        for (int i = tid - 384; i < kTabHdrWords; i += 128)
+          reinterpret_cast<uint32_t*>(a.tab)[i] = tab_header_word(a.bank, i);
+      for (int c = 4 * blockIdx.x + (warp - 12); c < 64; c += 4 * gridDim.x) tab_write_row(a.bank, a.tab, c, lane);
+    }
     const int quarter = warp & 3;
     const int m = 32 * quarter + lane;
     const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
@@ -470,6 +490,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[4] = clock64();
+    a.phase[5] = (long long)tc::global_timer_ns();
+  }
 }
 
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
@@ -485,7 +509,7 @@ size_t tc16_bwd_filter_partial_bytes(int C) {
 
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, uint8_t* filter_table) {
   BwdFilterTc16Args a;
   a.x = x;
   a.xsb = x_stride_b;
@@ -499,6 +523,10 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
   a.tiles_per_row = ceil_div64(T, F2_TILE);
   a.ntiles = B * a.tiles_per_row;
   a.status = tc_status_device_ptr();
+  a.phase = tc_phase_device_ptr();
+  if (a.phase) a.phase += 12;
+  a.bank = bank;
+  a.tab = (bank.C <= 64 && bank.K <= 256) ? filter_table : nullptr;
   if (!a.status) return cudaErrorInvalidSymbol;
   int64_t per_blk = di.sm_count / a.nblk;
   if (per_blk < 1) per_blk = 1;

@@ -72,6 +72,8 @@ struct BwdInputTc16Args {
   int64_t blocks_per_row;  // ceil(T / 128)
   int64_t nblocks;         // B * blocks_per_row
   int* status;
+  long long* phase;        // diagnostic time stamps (CTA 0), may be null
+  const uint8_t* tab;      // filter table left in the workspace by the grad-filter kernel (sinc_synth.cuh), or nullptr
 };
 
 // v0, v1 -> packed bf16 pairs (v1 in the high half): hi = RN(v), mid = RN(v - hi)
@@ -107,6 +109,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   const int64_t T = a.T;
 
   // ---------------- setup ------------------------------------------------------------------------------------
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[0] = clock64();
+    a.phase[1] = (long long)tc::global_timer_ns();
+  }
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&b_full[i], 4);
@@ -131,8 +137,38 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   __syncthreads();
   {
     float* wst = reinterpret_cast<float*>(ring);  // fp32 filters [c][256], rows >= C and taps >= K stay zero
-    for (int c = warp; c < C; c += H2_THREADS / 32)
-      synth_filter_warp(a.bank, c, lane, [&](int k, double w) { wst[c * 256 + k] = (float)w; });
+    // The filters come from the table the grad-filter kernel left in the workspace when that table provably belongs
+    // to this filter bank (header equal word for word, row checksums intact); otherwise every CTA synthesises them.
+    bool tab_ok = false;
+    if (a.tab) {
+      int good = tab_shape_ok(a.bank) ? 1 : 0;
+      if (good) {
+        const uint32_t* hdr = reinterpret_cast<const uint32_t*>(a.tab);
+        for (int i = tid; i < kTabHdrWords; i += H2_THREADS) good &= (hdr[i] == tab_header_word(a.bank, i)) ? 1 : 0;
+        const float4* src = reinterpret_cast<const float4*>(a.tab + kTabDataOff);
+        const unsigned long long* rowsum = reinterpret_cast<const unsigned long long*>(a.tab + kTabRowsumOff);
+        for (int c = warp; c < 64; c += H2_THREADS / 32) {
+          unsigned long long sum = 0ull;
+#pragma unroll
+          for (int q = lane; q < 64; q += 32) {
+            const float4 v = src[c * 64 + q];
+            reinterpret_cast<float4*>(wst)[c * 64 + q] = v;
+            sum += tab_mix(v.x, 4 * q) + tab_mix(v.y, 4 * q + 1) + tab_mix(v.z, 4 * q + 2) + tab_mix(v.w, 4 * q + 3);
+          }
+          good &= (warp_sum_u64(sum) == rowsum[c]) ? 1 : 0;
+        }
+      }
+      tab_ok = __syncthreads_and(good) != 0;
+      if (!tab_ok) {  // rejected: whatever was copied goes away again
+        for (int i = tid; i < 64 * 256 / 4; i += H2_THREADS)
+          reinterpret_cast<float4*>(wst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+      }
+    }
+    if (!tab_ok)
+      for (int c = warp; c < C; c += H2_THREADS / 32)
+        synth_filter_warp(a.bank, c, lane, [&](int k, double w) { wst[c * 256 + k] = (float)w; });
+    if (blockIdx.x == 0 && tid == 0 && a.phase) a.phase[12] = tab_ok ? 1 : 0;   // diagnostic: which source was used
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -169,6 +205,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   // ---------------- work: a contiguous range of 128-sample output blocks, cut into per-utterance runs ----------
   // Every role walks the same sequence of (run, stage) pairs.  The three roles are separate top-level branches
   // that never merge before the end of the kernel, so each keeps the register budget setmaxnreg gave it.
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[2] = clock64();
+    a.phase[3] = (long long)tc::global_timer_ns();
+  }
   const int64_t v0 = a.nblocks * blockIdx.x / gridDim.x;
   const int64_t v1 = a.nblocks * (blockIdx.x + 1) / gridDim.x;
   bool ok = true;
@@ -490,6 +530,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 12) tc::tmem_dealloc(tmem, 512);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[4] = clock64();
+    a.phase[5] = (long long)tc::global_timer_ns();
+  }
 }
 
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
@@ -528,7 +572,7 @@ bool make_grad_map(CUtensorMap* m, const void* g, int64_t B, int C, int64_t T) {
 }  // namespace
 
 cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
-                                  const DeviceInfo& di, cudaStream_t st) {
+                                  const DeviceInfo& di, cudaStream_t st, const uint8_t* filter_table) {
   BwdInputTc16Args a;
   a.bank = bank;
   a.g = gy;
@@ -538,6 +582,9 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   a.blocks_per_row = ceil_div64(T, H2_NS);
   a.nblocks = B * a.blocks_per_row;
   a.status = tc_status_device_ptr();
+  a.phase = tc_phase_device_ptr();
+  if (a.phase) a.phase += 6;
+  a.tab = filter_table;
   if (!a.status) return cudaErrorInvalidSymbol;
   int sms = di.sm_count - reserved_sms();  // data-parallel: a few SMs stay free for the all-reduce in flight
   if (sms < 1) sms = 1;

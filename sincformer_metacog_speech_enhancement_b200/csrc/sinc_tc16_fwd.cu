@@ -58,6 +58,7 @@ struct FwdTc16Args {
   int64_t B, T;
   int nblk;            // filter blocks of 16
   int ksteps;          // ceil((K + 7) / 16) <= 17
+  long long* phase;    // diagnostic time stamps (CTA 0), may be null
   int64_t tiles_per_row;
   int64_t ntiles;      // B * tiles_per_row (per filter block)
   int* status;
@@ -112,6 +113,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   const int64_t T = a.T;
 
   // ---------------- setup: barriers, TMEM, filters --------------------------------------------------
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[0] = clock64();
+    a.phase[1] = (long long)tc::global_timer_ns();
+  }
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&x_full[i], 1);
@@ -177,6 +182,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
 
   const int64_t my_tiles = slot < a.ntiles ? (a.ntiles - slot + per_blk - 1) / per_blk : 0;
   bool ok = true;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[2] = clock64();
+    a.phase[3] = (long long)tc::global_timer_ns();
+  }
 
   if (warp == 9) {
     // ---------------- producer: waveform tile -> max -> scale -> fp16 hi / lo in shared memory ---------------
@@ -353,6 +362,10 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 4) tc::tmem_dealloc(tmem, 512);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.phase) {
+    a.phase[4] = clock64();
+    a.phase[5] = (long long)tc::global_timer_ns();
+  }
 }
 
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di) {
@@ -377,6 +390,7 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
   a.tiles_per_row = ceil_div64(T, U_TT);
   a.ntiles = B * a.tiles_per_row;
   a.status = tc_status_device_ptr();
+  a.phase = tc_phase_device_ptr();
   a.gn_partial = reinterpret_cast<float2*>(gn_partial);
   if (!a.status) return cudaErrorInvalidSymbol;
   int64_t per_blk = di.sm_count / a.nblk;

@@ -30,6 +30,10 @@ namespace sinc {
 
 // set to 1 by any tcgen05 kernel whose barrier wait timed out (a protocol bug): read by sinc_tc_status()
 __device__ int g_tc_status = 0;
+// diagnostic time stamps of the last launch of each 16-bit tcgen05 kernel (CTA 0): {clock64, globaltimer ns} at
+// entry, after the prologue, at exit -- [0,6) forward, [6,12) grad-input, [12,18) grad-filter; [18] = 1 if that
+// grad-input launch took its filters from the workspace table (sinc_synth.cuh)
+__device__ long long g_tc_phase[20];
 
 constexpr int TF_THREADS = 224;  // warps 0-3 epilogue, 4 and 6 MMA issuers (even / odd tiles), 5 waveform producer
 constexpr int TF_FB = 32;                 // filters per CTA
@@ -292,6 +296,15 @@ int* tc_status_device_ptr() {
   void* p = nullptr;
   if (cudaGetSymbolAddress(&p, g_tc_status) != cudaSuccess) return nullptr;
   return reinterpret_cast<int*>(p);
+}
+
+long long* tc_phase_device_ptr() {
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, g_tc_phase) != cudaSuccess) return nullptr;
+  return reinterpret_cast<long long*>(p);
+}
+int read_tc_phase(long long* out20) {
+  return (int)cudaMemcpyFromSymbol(out20, g_tc_phase, 20 * sizeof(long long));
 }
 
 int read_tc_status(int* out) {

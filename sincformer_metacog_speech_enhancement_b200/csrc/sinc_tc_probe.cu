@@ -137,6 +137,9 @@ namespace sinc {
 
 struct RateArgs {
   int N, nacc, count, a_from_tmem;
+  int pattern;        // 0: one B descriptor; 1: forward-kernel sequence (17 K-steps x 3 products, B start += 32 bytes per
+                      // K-step, hi/lo operands); 2: the same with every B start address 128-byte aligned
+  int nonzero;        // operands filled with a non-trivial bit pattern (switching activity) instead of zeros
   long long* cycles;  // [1]
   int* status;
 };
@@ -146,7 +149,8 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   const int tid = threadIdx.x, warp = tid >> 5;
-  for (int i = tid; i < 16384 / 4; i += 128) reinterpret_cast<uint32_t*>(rsm)[i] = 0u;
+  for (int i = tid; i < 16384 / 4; i += 128)
+    reinterpret_cast<uint32_t*>(rsm)[i] = a.nonzero ? 0x3c003c00u ^ (uint32_t)(i * 0x9e3779b1u & 0x03ff03ffu) : 0u;
   if (tid == 0) {
     tc::mbar_init(&bar, 1);
     tc::mbar_init_fence();
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
   const uint32_t tm = slot;
   {  // zero the A columns [448, 512) of every lane
     uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (a.nonzero)
+      for (int j = 0; j < 8; ++j) z[j] = 0x3c003c00u ^ (uint32_t)((tid * 8 + j) * 0x85ebca6bu & 0x03ff03ffu);
     for (int c = 0; c < 64; c += 8) tc::tmem_st8(tm + ((uint32_t)(32 * warp) << 16) + 448 + c, z);
     tc::tmem_st_wait();
   }
@@ -175,9 +181,23 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
     const uint64_t bd = tc::desc_at(tc::make_smem_desc(16, 128), tc::uniform((int)tc::smem_addr(rsm)));
     const uint64_t ad = tc::desc_at(tc::make_smem_desc(16, 128), tc::uniform((int)tc::smem_addr(rsm + 8192)));
     long long t0 = 0;
+    const uint32_t b0 = tc::uniform((int)tc::smem_addr(rsm));  // (warp-wide shuffle: outside the elected-lane block)
     if (tc::elect_one()) {
       t0 = clock64();
       int acc = 0;
+      if (a.pattern) {
+        const uint64_t bd0 = tc::make_smem_desc(16, 128);
+        const uint32_t step = a.pattern == 1 ? 32u : 128u;
+        for (int i = 0; i < count; i += 51) {
+          for (int q = 0; q < 17; ++q) {
+            const uint64_t dh = tc::desc_at(bd0, b0 + step * q), dl = tc::desc_at(bd0, b0 + 4096 + step * q);
+            const uint32_t ah = tmu + 448 + 8 * (q & 3), al = ah + 32;
+            tc::mma_f16_ts(tmu, ah, dh, idesc, 1);
+            tc::mma_f16_ts(tmu, ah, dl, idesc, 1);
+            tc::mma_f16_ts(tmu, al, dh, idesc, 1);
+          }
+        }
+      } else
       for (int i = 0; i < count; ++i) {
         const uint32_t d = tmu + (uint32_t)(acc * N);
         if (a.a_from_tmem)
@@ -191,7 +211,7 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
     __syncwarp();
     const bool ok = tc::mbar_wait(&bar, 0);
     if (tc::elect_one()) {
-      a.cycles[0] = clock64() - t0;
+      if (blockIdx.x == 0) a.cycles[0] = clock64() - t0;
       if (!ok) *a.status = 1;
     }
     __syncwarp();
@@ -212,11 +232,13 @@ extern "C" int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, lon
   int r = get_device_info(&di);
   if (r) return r;
   if (di.cc_major != 10) return SINC_E_DEVICE;
-  RateArgs a{N, nacc, count, a_from_tmem, cycles_out, status};
+  // a_from_tmem: bit 0 = A operand in TMEM, bit 1 = non-zero operands, bits 2..3 = pattern, bits 8..15 = CTAs (0 = one)
+  const int grid = ((a_from_tmem >> 8) & 0xff) ? ((a_from_tmem >> 8) & 0xff) : 1;
+  RateArgs a{N, nacc, count, a_from_tmem & 1, (a_from_tmem >> 2) & 3, (a_from_tmem >> 1) & 1, cycles_out, status};
   const size_t smem = 16384 + 1024;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_mma_rate_kernel), (int)smem);
   if (e != cudaSuccess) return (int)e;
-  tc_mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(a);
+  tc_mma_rate_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(a);
   count_launch();
   return (int)cudaGetLastError();
 }

@@ -207,3 +207,60 @@ def test_tc16_bf16_activation_mode(B, T):
     fl, fb = param_floor(orc, o64["gfilt"].numpy())
     assert (dut.low_hz_.grad.cpu().double() - o64["g_low"]).abs().max() <= 1e-4 * o64["g_low"].abs().max() + fl
     assert (dut.band_hz_.grad.cpu().double() - o64["g_band"]).abs().max() <= 1e-4 * o64["g_band"].abs().max() + fb
+
+
+def _abi_backward(lib, m, ws, x, g, want_x, want_p):
+    from sincformer_metacog_speech_enhancement_b200.sinc import _bank
+    B, C, T = g.shape
+    fb = _bank(m.low_hz_.detach(), m.band_hz_.detach(), m.window, m.n_, m.sample_rate, m.min_low_hz, m.min_band_hz)
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    gx = torch.empty(B, 1, T, device=dev()) if want_x else None
+    gp = torch.empty(2, C, device=dev()) if want_p else None
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, P(gx), P(gp[0]) if want_p else None,
+                           P(gp[1]) if want_p else None, None, B, T, P(ws), ws.numel(), st)
+    assert rc == 0
+    torch.cuda.synchronize()
+    stamps = (ctypes.c_longlong * 20)()
+    assert lib.sinc_tc_phase_stamps(stamps) == 0
+    return gx, gp, int(stamps[18])
+
+
+def test_filter_table_in_workspace_is_validated():
+    """The grad-filter kernel leaves the synthesised filters in the workspace for the grad-input kernel
+    (sinc_synth.cuh).  The consumer must take them only when they provably belong to its filter bank: same call,
+    or an earlier parameter-gradient call with identical parameters -- never after the parameters changed or the
+    workspace bytes were overwritten."""
+    lib = _lib.load()
+    sb.set_engine("tc")
+    try:
+        torch.manual_seed(5)
+        B, C, K, T = 3, 64, 251, 4096
+        m = sb.SincConv1d(C, K, sample_rate=16000).to(dev())
+        x = torch.randn(B, 1, T, device=dev())
+        g = torch.randn(B, C, T, device=dev())
+        ws = torch.zeros(lib.sinc_workspace_bytes(B, T, C, K), dtype=torch.uint8, device=dev())
+        gx_cold, _, used = _abi_backward(lib, m, ws, x, g, True, False)
+        assert used == 0                                   # zeroed workspace: no table, filters synthesised in-kernel
+        gx_both, gp, used = _abi_backward(lib, m, ws, x, g, True, True)
+        assert used == 1                                   # one call: parameter gradients first, table consumed
+        assert torch.equal(gx_both, gx_cold)               # same fp32 taps either way: bit-identical grad-input
+        gx_split, _, used = _abi_backward(lib, m, ws, x, g, True, False)
+        assert used == 1 and torch.equal(gx_split, gx_cold)   # data-parallel order: table of the preceding call
+        # parameters change -> the header no longer matches -> synthesised in-kernel, and the result is the new one
+        with torch.no_grad():
+            m.band_hz_.mul_(1.03)
+        gx_new, _, used = _abi_backward(lib, m, ws, x, g, True, False)
+        assert used == 0 and not torch.equal(gx_new, gx_cold)
+        gx_new2, _, used = _abi_backward(lib, m, ws, x, g, True, True)
+        assert used == 1 and torch.equal(gx_new2, gx_new)
+        # workspace bytes overwritten behind a valid header (recycled allocation): the row checksum rejects the table
+        nfl = ws.numel() // 4
+        wsf = ws[: nfl * 4].view(torch.float32)
+        tail = wsf[-(64 * 256 + 64):]                      # inside the table rows (the table is the last region)
+        tail[1000:1004] += 1.0
+        gx_bad, _, used = _abi_backward(lib, m, ws, x, g, True, False)
+        assert used == 0 and torch.equal(gx_bad, gx_new)
+        assert tc_status() == 0
+    finally:
+        sb.set_engine("auto")

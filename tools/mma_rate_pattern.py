@@ -1,0 +1,19 @@
+"""tcgen05.mma rate for the forward kernel's operand sequence (see sinc_tc_probe.cu, RateArgs::pattern)."""
+import ctypes, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from sincformer_metacog_speech_enhancement_b200 import _lib
+lib = _lib.load()
+dev = torch.device("cuda:0")
+for N in (112, 64):
+    for pattern in (0, 1, 2):
+        cyc = torch.zeros(1, dtype=torch.int64, device=dev)
+        st = torch.zeros(1, dtype=torch.int32, device=dev)
+        count = 51 * 2000
+        flags = 1 | 2 | (pattern << 2) | (148 << 8)
+        for rep in range(2):
+            rc = lib.sinc_tc_mma_rate(N, 1, count, flags, ctypes.c_void_p(cyc.data_ptr()), ctypes.c_void_p(st.data_ptr()), None)
+            torch.cuda.synchronize()
+        print(json.dumps({"N": N, "pattern": pattern, "rc": rc, "status": int(st.item()),
+                          "cycles_per_mma": round(cyc.item() / count, 2)}), flush=True)

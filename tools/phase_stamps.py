@@ -1,0 +1,33 @@
+"""Where the time of each tcgen05 kernel goes at cfg 2: prologue vs main loop, and the SM clock the kernel really ran
+at (SM cycle counter / nanosecond timer, both read by CTA 0) -- steady-state back-to-back launches, like the bench."""
+import ctypes, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import sincformer_metacog_speech_enhancement_b200 as sb
+from sincformer_metacog_speech_enhancement_b200 import _lib
+from sincformer_metacog_speech_enhancement_b200.sinc import _bank
+
+dev = torch.device("cuda:0"); lib = _lib.load()
+C, K, T, B = 64, 251, 48000, 32
+m = sb.SincConv1d(C, K, sample_rate=16000).to(dev)
+fb = _bank(m.low_hz_.detach(), m.band_hz_.detach(), m.window, m.n_, m.sample_rate, m.min_low_hz, m.min_band_hz)
+P = lambda t: ctypes.c_void_p(t.data_ptr())
+x = torch.randn(B, 1, T, device=dev); y = torch.empty(B, C, T, device=dev); g = torch.randn(B, C, T, device=dev)
+gx = torch.empty(B, 1, T, device=dev); gp = torch.empty(2, C, device=dev)
+nbytes = lib.sinc_workspace_bytes(B, T, C, K); ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def step():
+    assert lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), 0, B, T, P(ws), nbytes, st) == 0
+    assert lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, P(gx), P(gp[0]), P(gp[1]), None, B, T, P(ws), nbytes, st) == 0
+for _ in range(200):     # ~90 ms of sustained load before the stamps that count
+    step()
+torch.cuda.synchronize()
+out = (ctypes.c_longlong * 20)()
+assert lib.sinc_tc_phase_stamps(out) == 0
+print(json.dumps({"grad_input_filters_from_table": int(out[18])}))
+for k, name in enumerate(("fwd", "bwd_input", "bwd_filter")):
+    c0, t0, c1, t1, c2, t2 = out[6 * k: 6 * k + 6]
+    print(json.dumps({"kernel": name, "prologue_us": (t1 - t0) / 1e3, "main_us": (t2 - t1) / 1e3,
+                      "prologue_cycles": c1 - c0, "main_cycles": c2 - c1,
+                      "sm_mhz": round((c2 - c0) / ((t2 - t0) / 1e3), 1)}), flush=True)
