@@ -56,7 +56,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -71,7 +71,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -90,7 +90,7 @@ class ClockSampler:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if not self.path or not os.path.exists(self.path):
             return out
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in open(self.path):
             f = [s.strip() for s in line.split(",")]
             if len(f) < 9:
@@ -100,6 +100,10 @@ class ClockSampler:
                 mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pw.append(0.0)
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
@@ -109,6 +113,9 @@ class ClockSampler:
             out["sm_mhz"] = statistics.median(busy)
             out["sm_max_mhz"] = max(mx)
             out["samples"] = len(sm)
+            busy_pw = [w for v, w in zip(sm, pw) if v >= 0.5 * max(sm) and w > 0]
+            if busy_pw:
+                out["power_w"] = max(busy_pw)
         out["reasons"] = sorted(reasons)
         return out
 
@@ -247,6 +254,21 @@ def run_ours(args):
         ms_total = timed(step_resident, args.steps, args.warmup)
         launches = (sb.kernel_launch_count() - n0) * args.steps // (args.steps + args.warmup)
     clocks = clk.summary()
+    # nvidia-smi reports the clock the driver ASKS for; under the combined tensor + HBM load of this path the SMs run
+    # slower (power management).  The kernels stamp the SM cycle counter and the nanosecond timer at entry and exit
+    # (CTA 0, last launch of the timed region): cycles / ns is the clock they really ran at.
+    try:
+        stamps = (ctypes.c_longlong * 20)()
+        if lib.sinc_tc_phase_stamps(stamps) == 0:
+            real = {}
+            for k, name in enumerate(("fwd", "bwd_input", "bwd_filter")):
+                c0, t0, c2, t2 = stamps[6 * k], stamps[6 * k + 1], stamps[6 * k + 4], stamps[6 * k + 5]
+                if t2 > t0 and c2 > c0:
+                    real[name] = round((c2 - c0) / ((t2 - t0) / 1e3), 1)
+            if real:
+                clocks["sm_mhz_in_kernel"] = real
+    except Exception:
+        pass
     ms_step = ms_total / args.steps
     value = world * audio_per_step / (ms_step * 1e-3)
 

@@ -33,8 +33,9 @@ __device__ __forceinline__ ChanCoef chan_coef(const Bank& bk, int c) {
   ChanCoef cc;
   cc.unclamped = pre <= nyq;
   const double high = pre > nyq ? nyq : pre;              // clamp(max=); NaN passes through
-  cc.f_lo = low / bk.sr;                                  // :95
-  cc.f_hi = high / bk.sr;                                 // :96
+  const double inv_sr = 1.0 / bk.sr;                      // one fp64 division (independent of the parameter loads)
+  cc.f_lo = low * inv_sr;                                 // :95   (differs from low / sr in the last bit of a double)
+  cc.f_hi = high * inv_sr;                                // :96
   return cc;
 }
 

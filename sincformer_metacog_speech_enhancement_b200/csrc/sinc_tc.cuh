@@ -148,9 +148,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_addr(bar)), "r"(parity)
+      : "r"(smem_addr(bar)), "r"(parity), "r"(2000u)   // suspend-time hint (ns): fewer polls while the phase is pending
       : "memory");
   return ok != 0;
 }

@@ -27,6 +27,8 @@
 // overlap the next window's MMAs.
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "sinc_internal.h"
 #include "sinc_synth.cuh"
 #include "sinc_tc.cuh"
@@ -282,14 +284,19 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   } else if (warp < 10) {
     // ------------- MMA issuers: warp 8 owns the shifts rho = 0,1, warp 9 rho = 2,3 -------------------------------
     // All lanes run the loop (warp-uniform control flow and operands); only the elected lane issues.
-    {
-      const int w = tc::uniform(warp - 8);
-      const int ntl = tc::uniform((int)my_tiles);
-      const int tpr = tc::uniform((int)a.tiles_per_row);
-      const int tile0 = tc::uniform((int)(tile_begin % a.tiles_per_row));
+    // The issue loop is instruction-bound (an N = 32 MMA occupies the tensor pipe for 16 cycles; tools/
+    // mma_rate_pattern.py reaches that rate from a lean instruction stream): everything the loop needs is kept
+    // provably warp-uniform -- derived from kernel parameters, blockIdx and compile-time constants, the issuer's
+    // identity is a template constant -- so that the compiler holds it in uniform registers, and the shared-memory
+    // descriptors are advanced by additions instead of being rebuilt from addresses.
+    auto issue = [&](auto wtag) {
+      constexpr int w = decltype(wtag)::value;
+      const int ntl = (int)my_tiles;
+      const int tpr = (int)a.tiles_per_row;
+      const int tile0 = (int)(tile_begin % a.tiles_per_row);
       const uint32_t idesc = tc::make_idesc_f16(128, F2_N, tc::kFmtBF16, tc::kFmtBF16);
       const uint64_t bdesc = tc::make_smem_desc(16, 128);  // in-place Toeplitz view, row pitch 8 samples
-      const uint32_t xs0 = tc::uniform((int)tc::smem_addr(xs));
+      const uint32_t xs0 = tc::smem_addr(xs);
       const uint32_t tm = tc::uniform((int)tmem);
       int cc = 0;          // ring slots consumed so far
       int ti = tile0;      // tile index within its utterance
@@ -320,15 +327,17 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           const int s = cc & (F2_RING - 1);
           ok = ok && tc::mbar_wait(&a_full[s], (uint32_t)((cc / F2_RING) & 1));
           tc::fence_after_sync();
+          const uint64_t dsc0 = tc::desc_at(bdesc, b0);
           if (tc::elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < F2_KPS; ++kk) {
               const uint32_t ah = tm + 2 * F2_DCOLS + 16 * F2_KPS * s + 16 * kk, am = ah + 8;
               // consecutive MMAs into the same accumulator serialise on its TMEM read-modify-write: alternate the
               // two shifts this issuer owns so that dependent instructions are never adjacent
-              const uint64_t bh0 = tc::desc_at(bdesc, b0 + 32 * kk), bm0 = tc::desc_at(bdesc, b0 + 32 * kk + F2_XLEN * 2);
-              const uint64_t bh1 = tc::desc_at(bdesc, b0 + 32 * kk + 2 * F2_XLEN * 2);
-              const uint64_t bm1 = tc::desc_at(bdesc, b0 + 32 * kk + 3 * F2_XLEN * 2);
+              // (descriptor start-address field = bytes >> 4: a byte offset is an addition to the low word)
+              const uint64_t bh0 = dsc0 + (uint64_t)((32 * kk) >> 4), bm0 = bh0 + (uint64_t)((F2_XLEN * 2) >> 4);
+              const uint64_t bh1 = bh0 + (uint64_t)((2 * F2_XLEN * 2) >> 4);
+              const uint64_t bm1 = bh0 + (uint64_t)((3 * F2_XLEN * 2) >> 4);
               const uint32_t acc0 = kk == 0 ? acc : 1u;
               tc::mma_f16_ts(d0, ah, bh0, idesc, acc0);
               tc::mma_f16_ts(d0 + F2_N, ah, bh1, idesc, acc0);
@@ -352,7 +361,11 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         }
         __syncwarp();
       }
-    }
+    };
+    if (warp == 8)
+      issue(std::integral_constant<int, 0>{});
+    else
+      issue(std::integral_constant<int, 1>{});
   } else if (warp == 10) {
     // ------------- waveform producer: four shifted bf16 hi/mid copies of the tile ---------------------------
     // xs_rho[i] = x[tb - H + i + rho].  Lane handles element pairs: even shifts store the pair (i, i+1) at word

@@ -156,11 +156,12 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   const uint32_t tmem = *tmem_slot;
 
   // W' -> TMEM: lane = row m = 8*cl + r, column = tap pair (s, s+1), W'[m, s] = w[cl, s - r]
-  if (warp < 4) {
-    const int m = tid, cl = m >> 3, r = m & 7;
-    const uint32_t base = tmem + ((uint32_t)(32 * warp) << 16);
+  // (two warps per TMEM lane quarter, alternate 16-tap column groups)
+  if (warp < 8) {
+    const int m = tid & 127, cl = m >> 3, r = m & 7;
+    const uint32_t base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     const float* wr = wsc + cl * U_WPITCH;
-    for (int s0 = 0; s0 < U_KS; s0 += 16) {
+    for (int s0 = 16 * (warp >> 2); s0 < U_KS; s0 += 32) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {

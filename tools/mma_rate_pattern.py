@@ -6,7 +6,7 @@ import torch
 from sincformer_metacog_speech_enhancement_b200 import _lib
 lib = _lib.load()
 dev = torch.device("cuda:0")
-for N in (112, 64):
+for N in (112, 64, 32, 16):
     for pattern in (0, 1, 2):
         cyc = torch.zeros(1, dtype=torch.int64, device=dev)
         st = torch.zeros(1, dtype=torch.int32, device=dev)
