@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
     const gvec zero4 = G::zero();
     gvec halo = zero4;  // the 4 samples before the current stage (h = 1 rows start 4 samples early)
+    const bool all_rows = __all_sync(0xffffffffu, row_valid);
     const uint8_t* gbytes = reinterpret_cast<const uint8_t*>(a.g);
     int64_t cc0 = 0;      // ring slots (chunks of F2_KPS K-steps) before the current tile
     int64_t gs = 0;       // staging stages consumed so far
@@ -250,16 +251,26 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           const int ch = (8 / F2_KPS) * st + pch;
           if (F2_KPS * ch < nq) {
             gvec v[4 * F2_KPS];
-#pragma unroll
-            for (int i = 0; i < 4 * F2_KPS; ++i) {
+            // Interior stage of a full filter block (the common case): no per-element range checks -- the 64-bit
+            // compares and selects of the general path were a third of the converters' instructions (ncu r04c),
+            // and the converters are co-critical with the MMAs.  (t < 0 never needs a check: the halo is zero at
+            // the start of an utterance.)
+            const bool interior = all_rows && ts + F2_GSAMP <= T;
+            auto fetch = [&](int i) -> gvec {
               const int off = 16 * F2_KPS * pch - 4 * h + 4 * i;  // sample offset within the stage (-4 only for pch = 0, h = 1)
-              const int64_t tj = ts + off;
-              gvec w;
-              if (pch == 0 && i == 0)
-                w = h ? halo : *reinterpret_cast<const gvec*>(rowp);
-              else
-                w = *reinterpret_cast<const gvec*>(rowp + G::esz * off);
-              v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
+              if (pch == 0 && i == 0) return h ? halo : *reinterpret_cast<const gvec*>(rowp);
+              return *reinterpret_cast<const gvec*>(rowp + G::esz * off);
+            };
+            if (interior) {
+#pragma unroll
+              for (int i = 0; i < 4 * F2_KPS; ++i) v[i] = fetch(i);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4 * F2_KPS; ++i) {
+                const int64_t tj = ts + (16 * F2_KPS * pch - 4 * h + 4 * i);
+                const gvec w = fetch(i);
+                v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
+              }
             }
             emit(v, cc0 + ch);
           }
