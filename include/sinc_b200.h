@@ -12,7 +12,10 @@
  *     asynchronous on it, the library never synchronises the device;
  *   - the library allocates nothing and frees nothing: the caller owns x, y, grads and the
  *     workspace (size from sinc_workspace_bytes), and may reuse the workspace across calls that
- *     are ordered on one stream;
+ *     are ordered on one stream.  The workspace needs no initialisation and carries no state the
+ *     caller must preserve: besides scratch it holds a self-validating copy of the synthesised
+ *     filters (written by a parameter-gradient call, used by a later grad-input call only if its
+ *     header matches that call's filter bank word for word and its checksums hold);
  *   - return value: 0 = success, < 0 = argument error (SINC_E_*), > 0 = a cudaError_t;
  *     sinc_strerror() turns either into text.  Nothing throws or exits across this boundary;
  *   - C = out_channels, K = kernel_size (odd; the reference bumps even K to K+1 in __init__,

@@ -3,6 +3,8 @@
 // matrix descriptors (without the start address) and the instruction descriptor; the kernel runs `ksteps`
 // MMAs into one accumulator and returns D[128][N].  This is how the in-place Toeplitz descriptors
 // (overlapping core matrices, LBO = 16 B) and the TMEM A-operand layout were validated on B200.
+#include <type_traits>
+
 #include "sinc_internal.h"
 #include "sinc_tc.cuh"
 
@@ -139,6 +141,8 @@ struct RateArgs {
   int N, nacc, count, a_from_tmem;
   int pattern;        // 0: one B descriptor; 1: forward-kernel sequence (17 K-steps x 3 products, B start += 32 bytes per
                       // K-step, hi/lo operands); 2: the same with every B start address 128-byte aligned
+  int stress;         // what warps 1-3 do meanwhile: 0 nothing, 1 tcgen05.st into unused TMEM columns, 2 LDS.128 from the
+                      // B operand's shared memory, 3 tcgen05.ld of the accumulator columns
   int nonzero;        // operands filled with a non-trivial bit pattern (switching activity) instead of zeros
   long long* cycles;  // [1]
   int* status;
@@ -146,13 +150,14 @@ struct RateArgs {
 
 __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
   extern __shared__ __align__(1024) uint8_t rsm[];  // B: 256 rows x 32 bytes (zeros), A (SS form): 128 rows x 32 bytes
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar, bar2;   // bar2: target of the extra commits of pattern 3 (never waited on)
   __shared__ uint32_t slot;
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < 16384 / 4; i += 128)
     reinterpret_cast<uint32_t*>(rsm)[i] = a.nonzero ? 0x3c003c00u ^ (uint32_t)(i * 0x9e3779b1u & 0x03ff03ffu) : 0u;
   if (tid == 0) {
     tc::mbar_init(&bar, 1);
+    tc::mbar_init(&bar2, 1000000);
     tc::mbar_init_fence();
   }
   if (warp == 0) {
@@ -185,16 +190,41 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
     if (tc::elect_one()) {
       t0 = clock64();
       int acc = 0;
-      if (a.pattern) {
+      if (a.pattern == 3) {
+        // the forward sequence with a tcgen05.commit (to a barrier nobody waits on) every KC K-steps = 3*KC MMAs:
+        // the kernels commit to release ring slots -- does that cost the tensor pipe anything?
         const uint64_t bd0 = tc::make_smem_desc(16, 128);
-        const uint32_t step = a.pattern == 1 ? 32u : 128u;
+        auto body = [&](auto kc) {
+          constexpr int KC = decltype(kc)::value;
+          for (int i = 0; i < count; i += 51) {
+#pragma unroll
+            for (int q = 0; q < 17; ++q) {
+              const uint64_t dh = tc::desc_at(bd0, b0 + 32 * q), dl = tc::desc_at(bd0, b0 + 4096 + 32 * q);
+              const uint32_t ah = tmu + 448 + 8 * (q & 3), al = ah + 32;
+              tc::mma_f16_ts(tmu, ah, dh, idesc, 1);
+              tc::mma_f16_ts(tmu, ah, dl, idesc, 1);
+              tc::mma_f16_ts(tmu, al, dh, idesc, 1);
+              if (q % KC == KC - 1) tc::mma_commit(&bar2);
+            }
+          }
+        };
+        if (nacc == 1) body(std::integral_constant<int, 1>{});
+        else if (nacc == 2) body(std::integral_constant<int, 2>{});
+        else if (nacc == 4) body(std::integral_constant<int, 4>{});
+        else body(std::integral_constant<int, 8>{});
+      } else if (a.pattern) {
+        const uint64_t bd0 = tc::make_smem_desc(16, 128);
+        const uint32_t step = a.pattern == 2 ? 128u : 32u;
         for (int i = 0; i < count; i += 51) {
           for (int q = 0; q < 17; ++q) {
             const uint64_t dh = tc::desc_at(bd0, b0 + step * q), dl = tc::desc_at(bd0, b0 + 4096 + step * q);
             const uint32_t ah = tmu + 448 + 8 * (q & 3), al = ah + 32;
-            tc::mma_f16_ts(tmu, ah, dh, idesc, 1);
-            tc::mma_f16_ts(tmu, ah, dl, idesc, 1);
-            tc::mma_f16_ts(tmu, al, dh, idesc, 1);
+            // nacc = 1: one accumulator; nacc = 2: consecutive MMAs alternate between two accumulators (the
+            // grad-filter issue order); nacc = 3: runs of three MMAs per accumulator, two accumulators
+            const uint32_t d1 = tmu + (uint32_t)N;
+            tc::mma_f16_ts(nacc == 3 && (q & 1) ? d1 : tmu, ah, dh, idesc, 1);
+            tc::mma_f16_ts(nacc == 2 ? d1 : (nacc == 3 && (q & 1) ? d1 : tmu), ah, dl, idesc, 1);
+            tc::mma_f16_ts(nacc == 3 && (q & 1) ? d1 : tmu, al, dh, idesc, 1);
           }
         }
       } else
@@ -213,8 +243,36 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
     if (tc::elect_one()) {
       if (blockIdx.x == 0) a.cycles[0] = clock64() - t0;
       if (!ok) *a.status = 1;
+      *reinterpret_cast<volatile uint32_t*>(&slot) = 0xffffffffu;  // stops the background traffic of warps 1-3
     }
     __syncwarp();
+  }
+  else if (a.stress) {
+    // background traffic until warp 0 reports (the flag is the cycle count it writes at the end)
+    volatile uint32_t* done = &slot;  // reused as the 'finished' flag: warp 0 sets it to 0xffffffff
+    uint32_t z[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+    uint32_t sink = 0;
+    const uint32_t lb = ((uint32_t)(32 * warp) << 16);
+    while (*done != 0xffffffffu) {
+      for (int r = 0; r < 16; ++r) {
+        if (a.stress == 1) {
+          tc::tmem_st8(tm + lb + 384 + 8 * (r & 7), z);
+        } else if (a.stress == 2) {
+          uint32_t v0, v1, v2, v3;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3)
+                       : "r"(tc::smem_addr(rsm + 16 * ((tid + 37 * r) & 511))));
+          sink += v0 + v3;
+        } else {
+          uint32_t v[8];
+          tc::tmem_ld8(tm + lb + 8 * (r & 7), v);
+          tc::tmem_ld_wait();
+          sink += v[0];
+        }
+      }
+      if (a.stress == 1) tc::tmem_st_wait();
+    }
+    if (sink == 0x12345678u) a.cycles[0] = 0;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -232,9 +290,11 @@ extern "C" int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, lon
   int r = get_device_info(&di);
   if (r) return r;
   if (di.cc_major != 10) return SINC_E_DEVICE;
-  // a_from_tmem: bit 0 = A operand in TMEM, bit 1 = non-zero operands, bits 2..3 = pattern, bits 8..15 = CTAs (0 = one)
+  // a_from_tmem: bit 0 = A operand in TMEM, bit 1 = non-zero operands, bits 2..3 = pattern, bits 4..5 = background
+  // traffic of the other warps (RateArgs::stress), bits 8..15 = CTAs (0 = one)
   const int grid = ((a_from_tmem >> 8) & 0xff) ? ((a_from_tmem >> 8) & 0xff) : 1;
-  RateArgs a{N, nacc, count, a_from_tmem & 1, (a_from_tmem >> 2) & 3, (a_from_tmem >> 1) & 1, cycles_out, status};
+  RateArgs a{N, nacc, count, a_from_tmem & 1, (a_from_tmem >> 2) & 3, (a_from_tmem >> 4) & 3, (a_from_tmem >> 1) & 1,
+             cycles_out, status};
   const size_t smem = 16384 + 1024;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_mma_rate_kernel), (int)smem);
   if (e != cudaSuccess) return (int)e;
