@@ -162,7 +162,21 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// One phase check without a suspend-time hint.  Any mbarrier phase check has ~160 cycles of latency even when the
+// phase is already complete (tools/mbar_wait_cost.py: try_wait 162, test_wait 156, try_wait with a hint 210), so the
+// MMA issuers call this EARLY -- for the barrier of their next step, before issuing the MMAs of the current one -- and
+// read the result afterwards: the latency hides behind the issue work instead of sitting between two batches of MMAs.
+__device__ __forceinline__ bool mbar_try_wait_plain(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_addr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_plain(bar, parity)) return true;  // the common case in a well-fed pipeline
   // fast path: no timer access while the barrier flips within a few thousand polls (the normal case)
 #pragma unroll 1
   for (int spin = 0; spin < 4096; ++spin)

@@ -279,7 +279,49 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
   if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
+// ---- what a wait on an ALREADY COMPLETED mbarrier phase costs (cycles per wait, one thread, dependent chain) ----
+// mode 0: mbarrier.try_wait with the suspend-time hint (tc::mbar_try_wait), 1: try_wait without a hint,
+// 2: mbarrier.test_wait (non-blocking), 3: tc::mbar_wait (the kernels' bounded wait: test_wait, then try_wait polls)
+__global__ void __launch_bounds__(32, 1) mbar_cost_kernel(int mode, int count, long long* cycles) {
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    tc::mbar_init(&bar, 1);
+    tc::mbar_init_fence();
+    tc::mbar_arrive(&bar);  // phase 0 complete: waiting for parity 0 succeeds at once
+  }
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    const uint32_t addr = tc::smem_addr(&bar);
+    uint32_t acc = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {
+      uint32_t ok = 0;
+      if (mode == 0) {
+        ok = tc::mbar_try_wait(&bar, acc & 0u) ? 1u : 0u;
+      } else if (mode == 1) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(addr), "r"(acc & 0u) : "memory");
+      } else if (mode == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(addr), "r"(acc & 0u) : "memory");
+      } else {
+        ok = tc::mbar_wait(&bar, acc & 0u) ? 1u : 0u;
+      }
+      acc += ok;  // the next wait depends on this one
+    }
+    cycles[0] = clock64() - t0;
+    cycles[1] = acc;
+  }
+}
+
 }  // namespace sinc
+
+extern "C" int sinc_mbar_wait_cost(int mode, int count, long long* cycles_out2, void* stream) {
+  if (!cycles_out2 || count < 1 || mode < 0 || mode > 3) return SINC_E_SHAPE;
+  sinc::mbar_cost_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mode, count, cycles_out2);
+  sinc::count_launch();
+  return (int)cudaGetLastError();
+}
 
 extern "C" int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, long long* cycles_out, int* status,
                                 void* stream) {
