@@ -160,6 +160,12 @@ int sinc_tc_status(int* status_host);
  * workspace, 0 if it synthesised them.  Synchronises the device. */
 int sinc_tc_phase_stamps(long long* out20);
 
+/* Diagnostic: cycles per wait on an ALREADY COMPLETED mbarrier phase, one thread, dependent chain of `count` waits.
+ * mode 0: mbarrier.try_wait with a suspend-time hint, 1: try_wait, 2: test_wait, 3: the kernels' bounded wait.
+ * cycles_out2[0] = total SM cycles, [1] = number of waits that succeeded.  (Measured: 210 / 162 / 156 / 184 -- why
+ * the pipelines are built to need few phase checks per unit of work.) */
+int sinc_mbar_wait_cost(int mode, int count, long long* cycles_out2, void* stream);
+
 /* Diagnostic: run `ksteps` tcgen05.mma (kind::tf32, M = 128) on caller-supplied shared-memory images and
  * raw matrix / instruction descriptors and return the 128 x N accumulator.  Not part of the replacement
  * surface (the reference has no counterpart); it exists so the operand layouts the tensor-core engine
@@ -170,9 +176,14 @@ int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int bytesB, un
                   int a_from_tmem, int a_cols, int N, float* D_out, int* status_out, void* stream);
 
 
-/* Diagnostic: cycles one SM needs for `count` back-to-back tcgen05.mma (kind::f16, M = 128, N as given) issued by one
- * thread, rotating through `nacc` accumulators, A from TMEM (1) or shared memory (0).  No counterpart in the
- * reference; used by tools/mma_rate.py to size the kernels' MMA shapes. */
+/* Diagnostic: cycles per tcgen05.mma (kind::f16, M = 128, N as given), `count` of them issued by one thread; the SM
+ * cycle count of CTA 0 goes to cycles_out[0].  `a_from_tmem` is a bit field: bit 0 = A operand in TMEM (else shared
+ * memory); bit 1 = non-zero operand data; bits 2..3 = instruction pattern (0: generic loop rotating through `nacc`
+ * accumulators; 1: the forward kernel's sequence -- 17 K-steps x 3 products, B start += 32 bytes per K-step, `nacc` =
+ * 1 one accumulator / 2 alternating / 3 runs of three; 2: the same with 128-byte aligned B starts; 3: pattern 1 with
+ * a tcgen05.commit every `nacc` K-steps); bits 4..5 = what the CTA's other warps do meanwhile (0 nothing, 1
+ * tcgen05.st, 2 LDS.128, 3 tcgen05.ld); bits 8..15 = number of CTAs (0 = one).  No counterpart in the reference;
+ * tools/mma_rate*.py use it to establish what the tensor pipe costs and what it does not mind. */
 int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, long long* cycles_out, int* status_out, void* stream);
 
 #ifdef __cplusplus

@@ -22,6 +22,7 @@ ABI_SYMBOLS = (
     "sinc_forward", "sinc_backward", "sinc_tc_probe", "sinc_tc_status",
     "sinc_forward_gn", "sinc_forward_gn_partials", "sinc_gn_chunks", "sinc_gn_stats", "sinc_gn_gelu_forward",
     "sinc_gn_gelu_backward", "sinc_tc_mma_rate", "sinc_set_reserved_sms", "sinc_tc_phase_stamps",
+    "sinc_mbar_wait_cost",
 )
 
 
@@ -89,6 +90,8 @@ def _declare(lib):
                                           c.c_void_p]
     lib.sinc_tc_mma_rate.restype = c.c_int
     lib.sinc_tc_mma_rate.argtypes = [c.c_int, c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.sinc_mbar_wait_cost.restype = c.c_int
+    lib.sinc_mbar_wait_cost.argtypes = [c.c_int, c.c_int, c.c_void_p, c.c_void_p]
     lib.sinc_tc_phase_stamps.restype = c.c_int
     lib.sinc_tc_phase_stamps.argtypes = [c.POINTER(c.c_longlong)]
     lib.sinc_tc_status.restype = c.c_int

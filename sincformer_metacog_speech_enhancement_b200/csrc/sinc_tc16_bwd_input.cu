@@ -23,10 +23,12 @@
 // MMA flops per value).  Sums are carried across the two 32-column chunks in registers, the eight warps'
 // 128-cell windows and the carry from earlier stages are combined in a fixed order: bitwise reproducible.
 //
-// Pipeline: 4 producer warps (global -> bf16 hi/mid -> planes, 4-slot ring; the last row of a stage is also the
-// halo row of the next), 2 MMA issuer warps (one per 64-column half), double-buffered accumulators in TMEM,
-// 8 epilogue warps.  A CTA owns a contiguous range of 128-sample output blocks and recomputes the 2H-column halo
-// at the start of each run.
+// Pipeline: 4 producer warps (fp32 grad_y: TMA tensor boxes -> registers -> bf16 hi/mid -> planes; bf16 grad_y:
+// direct loads; 2-slot operand ring, the last row of a stage is also the halo row of the next), 1 MMA issuer warp
+// (the two 64-column halves of a stage one after the other), double-buffered accumulators in TMEM, 8 epilogue warps,
+// 3 combiner warps.  A CTA owns a contiguous range of 128-sample output blocks and recomputes the 2H-column halo at
+// the start of each run.  The filters come from the workspace table of the grad-filter kernel when it is valid
+// (sinc_synth.cuh), else every CTA synthesises them.
 #include <cuda.h>
 #include <cuda_bf16.h>
 

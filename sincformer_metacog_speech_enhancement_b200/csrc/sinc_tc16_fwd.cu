@@ -21,8 +21,9 @@
 // Every MMA takes A from TMEM; shared memory only serves the 3.5 KB B operand (64 B/clk).
 //
 // Warp roles (352 threads): warps 0-7 epilogue (two per TMEM lane quarter, 56 columns each: TMEM -> scale ->
-// phase-interleaved staging -> 1-D bulk stores of 3.5 KB rows), warps 8 and 10 MMA issuers (even / odd tiles,
-// warp-uniform issue loops), warp 9 waveform producer (global -> max -> scale -> fp16 hi/lo -> smem).
+// phase-interleaved staging -> 1-D bulk stores of 3.5 KB rows; plain global stores straight from the registers were
+// measured and are slower: main loop 158k -> 182k cycles), warp 8 MMA issuer (warp-uniform issue loop), warp 9
+// waveform producer (global -> max -> scale -> fp16 hi/lo -> smem), warp 10 idle after the prologue.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -32,7 +33,7 @@
 
 namespace sinc {
 
-constexpr int U_THREADS = 352;  // warps 0-7 epilogue (lane quarter = w%4, column half = w/4), 8 and 10 MMA issuers, 9 waveform producer
+constexpr int U_THREADS = 352;  // warps 0-7 epilogue (lane quarter = w%4, column half = w/4), 8 MMA issuer, 9 waveform producer
 constexpr int U_FB = 16;                  // filters per CTA
 constexpr int U_NJ = 112;                 // MMA N: output groups of 8 samples per tile
 constexpr int U_TT = 8 * U_NJ;            // 896 output samples per tile
