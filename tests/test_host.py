@@ -98,6 +98,8 @@ def test_abi_non_compute_calls():
     assert b"NULL" in lib.sinc_strerror(-1)
     assert b"odd K" in lib.sinc_strerror(-2)
     assert lib.sinc_workspace_bytes(32, 48000, 64, 251) >= 64 * 256 * 4
+    # the workspace also holds the self-validating filter table (header + W[64][256]) behind the partial tiles
+    assert lib.sinc_workspace_bytes(1, 1, 4, 3) >= 4096 + 64 * 256 * 4
     assert lib.sinc_workspace_bytes(1, 1, 70, 300) > lib.sinc_workspace_bytes(1, 1, 64, 251)
     assert lib.sinc_set_engine(7) == -8
     assert lib.sinc_set_engine(0) == 0 and lib.sinc_get_engine() == 0
