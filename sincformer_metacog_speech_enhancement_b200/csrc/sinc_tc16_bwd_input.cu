@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
       tc::mbar_init(&win_empty[i], 3);
     }
     for (int i = 0; i < 8; ++i) tc::mbar_init(&st_full[i], 1);
-    if constexpr (!GB) tc::tensormap_prefetch(&gmap);
+    tc::tensormap_prefetch(&gmap);
     tc::mbar_init_fence();
   }
   if (warp == 12) {
@@ -191,8 +191,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
           // fp32 grad_y: plane cq holds its filter pairs rotated by (cq & 3) -- the order in which the
           // producers read them conflict-free out of the swizzled staging boxes; W' follows the same order
           const int cq = 2 * cg + (j >> 2);
-          const int c = GB ? 16 * cg + 2 * j : 8 * cq + ((2 * (j & 3) + 2 * (cq & 3)) & 7);
-          split_bf16x2(wst[c * 256 + 2 * kp + e], wst[(c + 1) * 256 + 2 * kp + e], hi[j], mid[j]);
+          const int rot = GB ? (cq & 3) : 2 * (cq & 3);   // see the producers: rotation of the filter order per plane
+          const int ca = 8 * cq + ((2 * (j & 3) + rot) & 7), cb = 8 * cq + ((2 * (j & 3) + 1 + rot) & 7);
+          split_bf16x2(wst[ca * 256 + 2 * kp + e], wst[cb * 256 + 2 * kp + e], hi[j], mid[j]);
         }
         tc::tmem_st8(tmem + lane_base + 256 + 32 * e + 8 * cg, hi);
         tc::tmem_st8(tmem + lane_base + 320 + 32 * e + 8 * cg, mid);
@@ -246,7 +247,11 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
     // reads row 8cq + ((j + 2fg) & 7), 16-byte chunk pg ^ row: 8 distinct bank groups per quarter-warp.
     // bf16 grad_y keeps the direct global loads (LDG.64 of 4 positions, next stage in flight during the wait).
     const int pw = warp - 8;
-    const int fg = lane & 3, pg = lane >> 2;  // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups
+    // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups.  bf16 grad_y: the position groups
+    // of a half-warp are {0,1,4,5} / {2,3,6,7}, so that the LDS.64 of a half-warp cover all four 16-byte chunks
+    const int fg = lane & 3;
+    const int pg = GB ? ((lane >> 2) & 1) | (((lane >> 2) & 2) << 1) | (((lane >> 2) & 4) >> 1) : lane >> 2;
+    constexpr int BOXB = GB ? H2_STG_BOX / 2 : H2_STG_BOX;   // bytes of one box: 64 rows x 32 positions
     const int n0 = 32 * pw + 4 * pg;          // first of this thread's four columns within the stage
     const uint32_t stg0 = tc::smem_addr(smem + H2_SM_STG + pw * 2 * H2_STG_BOX);
     uint64_t* my_full = st_full + 2 * pw;
@@ -260,50 +265,43 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
       constexpr int ESZ = GB ? 2 : 4;
       const uint8_t* gb = reinterpret_cast<const uint8_t*>(a.g) + (b * C) * T * ESZ;
       gvec vv[16];
-      auto load_stage = [&](int64_t p) {  // bf16 path.  p = position of column n0 (a multiple of 4; T % 4 == 0)
-        const bool in = p >= 0 && p < T;
-        const uint8_t* q = gb + ((in ? p : 0) + (int64_t)(8 * fg) * T) * ESZ;  // one running row pointer: no address array
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int c = 8 * fg + (j & 7) + 32 * (j >> 3);
-          if constexpr (GB)
-            vv[j] = (in && c < C) ? __ldg(reinterpret_cast<const uint2*>(q)) : make_uint2(0u, 0u);
-          q += ((j == 7) ? 25 * T : T) * ESZ;
-        }
-      };
       auto issue_box = [&](int i, uint32_t q) {  // stage i of this run -> box q & 1 (the whole warp calls; one lane issues)
         if (tc::elect_one()) {
           uint64_t* bar = &my_full[q & 1];
-          tc::mbar_expect_tx(bar, H2_STG_BOX);
+          tc::mbar_expect_tx(bar, BOXB);
           tc::tensor_load_3d(stg0 + (q & 1) * H2_STG_BOX, &gmap, (int)(c0 + (int64_t)H2_NS * i + 32 * pw), 0, (int)b, bar);
         }
         __syncwarp();
       };
-      if constexpr (!GB) {
-        issue_box(0, ldq);
-        if (nst > 1) issue_box(1, ldq + 1);
-      }
+      issue_box(0, ldq);
+      if (nst > 1) issue_box(1, ldq + 1);
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
         const int slot = (int)(sg & 1);
-        if constexpr (!GB) {
+        {
           ok = ok && tc::mbar_wait(&my_full[ldq & 1], (ldq >> 1) & 1);
           const uint32_t box = stg0 + (ldq & 1) * H2_STG_BOX;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int cq = fg + 4 * (j >> 3);
-            const int r7 = ((j & 7) + 2 * fg) & 7;
-            const uint32_t addr = box + (8 * cq + r7) * 128 + ((pg ^ r7) << 4);
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(vv[j].x), "=f"(vv[j].y), "=f"(vv[j].z), "=f"(vv[j].w)
-                         : "r"(addr)
-                         : "memory");
+            if constexpr (GB) {
+              // 64-byte rows, 64-byte swizzle (16-byte chunk ^= bits 7..8 of the offset = (row >> 1) & 3); rows rotated
+              // by fg so that the 16 lanes of a half-warp read 16 distinct 8-byte bank pairs
+              const int r7 = ((j & 7) + fg) & 7;
+              const uint32_t addr = box + (8 * cq + r7) * 64 + ((((pg >> 1) ^ (r7 >> 1)) & 3) << 4) + (pg & 1) * 8;
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(vv[j].x), "=r"(vv[j].y) : "r"(addr) : "memory");
+            } else {
+              const int r7 = ((j & 7) + 2 * fg) & 7;
+              const uint32_t addr = box + (8 * cq + r7) * 128 + ((pg ^ r7) << 4);
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(vv[j].x), "=f"(vv[j].y), "=f"(vv[j].z), "=f"(vv[j].w)
+                           : "r"(addr)
+                           : "memory");
+            }
           }
           __syncwarp();
           if (i + 2 < nst) issue_box(i + 2, ldq + 2);  // same box: its contents are in registers now
           ++ldq;
-        } else {
-          if (i == 0) load_stage(c0 + n0);
         }
         // slot sg & 1 was last read by the MMAs of stage sg - 2
         if (sg >= 2) ok = ok && tc::mbar_wait(&b_empty[slot], (uint32_t)(((sg - 2) >> 1) & 1));
@@ -313,18 +311,20 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
             const int64_t p = c0 - 1;
             const bool in = p >= 0 && p < T;
             const int hq = lane >> 2;                                                      // plane
-            const int hc = GB ? 2 * lane : 8 * hq + ((2 * (lane & 3) + 2 * (hq & 3)) & 7);  // first filter of the pair
+            const int hrot = GB ? (hq & 3) : 2 * (hq & 3);
+            const int hc = 8 * hq + ((2 * (lane & 3) + hrot) & 7);       // the pair of filters of this word (see W')
+            const int hc1 = 8 * hq + ((2 * (lane & 3) + 1 + hrot) & 7);
             uint32_t h, m;
             if constexpr (GB) {
               const uint16_t* g16 = reinterpret_cast<const uint16_t*>(gb);
               const uint32_t w0 = (in && hc < C) ? __ldg(g16 + (int64_t)hc * T + p) : 0u;
-              const uint32_t w1 = (in && hc + 1 < C) ? __ldg(g16 + (int64_t)(hc + 1) * T + p) : 0u;
+              const uint32_t w1 = (in && hc1 < C) ? __ldg(g16 + (int64_t)hc1 * T + p) : 0u;
               h = w0 | (w1 << 16);
               m = 0u;
             } else {
               const float* g32 = reinterpret_cast<const float*>(gb);
               const float w0 = (in && hc < C) ? __ldg(g32 + (int64_t)hc * T + p) : 0.f;
-              const float w1 = (in && hc + 1 < C) ? __ldg(g32 + (int64_t)(hc + 1) * T + p) : 0.f;
+              const float w1 = (in && hc1 < C) ? __ldg(g32 + (int64_t)hc1 * T + p) : 0.f;
               split_bf16x2(w0, w1, h, m);
             }
             *reinterpret_cast<uint32_t*>(base + hq * H2_PLANE + (lane & 3) * 4) = h;
@@ -372,9 +372,6 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
               }
             }
           }
-        }
-        if constexpr (GB) {
-          if (i + 1 < nst) load_stage(c0 + (int64_t)H2_NS * (i + 1) + n0);  // in flight during the next wait
         }
         tc::fence_async_smem();
         __syncwarp();
@@ -539,7 +536,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
 }
 
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
-  return C <= 64 && K <= 256 && T % 4 == 0 && (g_dtype == SINC_DTYPE_F32 || g_dtype == SINC_DTYPE_BF16) &&
+  // (the rows of the TMA tensor map must be 16-byte aligned: T % 4 for fp32, T % 8 for bf16 grad_y)
+  const bool rows_ok = g_dtype == SINC_DTYPE_F32 ? T % 4 == 0 : (g_dtype == SINC_DTYPE_BF16 && T % 8 == 0);
+  return C <= 64 && K <= 256 && rows_ok &&
          reinterpret_cast<uintptr_t>(g) % 16 == 0 && di.max_smem_optin >= H2_SM_TOTAL + 1024;
 }
 
@@ -559,16 +558,19 @@ EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-// grad_y [B][C][T] fp32 as a 3-D tensor (T fastest); box = 32 positions x 64 filters of one utterance, 128-byte swizzle
-bool make_grad_map(CUtensorMap* m, const void* g, int64_t B, int C, int64_t T) {
+// grad_y [B][C][T] as a 3-D tensor (T fastest); box = 32 positions x 64 filters of one utterance, swizzle = the
+// row length of the box (128 bytes fp32, 64 bytes bf16)
+bool make_grad_map(CUtensorMap* m, const void* g, bool bf16, int64_t B, int C, int64_t T) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
+  const cuuint64_t esz = bf16 ? 2 : 4;
   const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {(cuuint64_t)T * 4, (cuuint64_t)T * 4 * (cuuint64_t)C};
+  const cuuint64_t strides[2] = {(cuuint64_t)T * esz, (cuuint64_t)T * esz * (cuuint64_t)C};
   const cuuint32_t box[3] = {32, 64, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g), dims, strides, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g), dims,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace
@@ -597,7 +599,7 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   if (e != cudaSuccess) return e;
   CUtensorMap gmap;
   memset(&gmap, 0, sizeof(gmap));
-  if (gy_dtype != SINC_DTYPE_BF16 && !make_grad_map(&gmap, gy, B, bank.C, T)) return cudaErrorNotSupported;
+  if (!make_grad_map(&gmap, gy, gy_dtype == SINC_DTYPE_BF16, B, bank.C, T)) return cudaErrorNotSupported;
   kern<<<grid, H2_THREADS, smem, st>>>(a, gmap);
   count_launch();
   return cudaGetLastError();
