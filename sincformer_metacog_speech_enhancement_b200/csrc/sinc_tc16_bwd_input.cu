@@ -23,8 +23,8 @@
 // MMA flops per value).  Sums are carried across the two 32-column chunks in registers, the eight warps'
 // 128-cell windows and the carry from earlier stages are combined in a fixed order: bitwise reproducible.
 //
-// Pipeline: 4 producer warps (fp32 grad_y: TMA tensor boxes -> registers -> bf16 hi/mid -> planes; bf16 grad_y:
-// direct loads; 2-slot operand ring, the last row of a stage is also the halo row of the next), 1 MMA issuer warp
+// Pipeline: 4 producer warps (TMA tensor boxes -> registers -> bf16 hi/mid -> planes, for fp32 and bf16 grad_y alike;
+// 2-slot operand ring, the last row of a stage is also the halo row of the next), 1 MMA issuer warp
 // (the two 64-column halves of a stage one after the other), double-buffered accumulators in TMEM, 8 epilogue warps,
 // 3 combiner warps.  A CTA owns a contiguous range of 128-sample output blocks and recomputes the 2H-column halo at
 // the start of each run.  The filters come from the workspace table of the grad-filter kernel when it is valid
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
     // as it has read it into registers -- global-load latency is off the conversion path and the L1 data pipe moves
     // 128-byte wavefronts (LDS.128 of the box) instead of one wavefront per 32-byte sector of an LDG.  Lane (fg, pg)
     // reads row 8cq + ((j + 2fg) & 7), 16-byte chunk pg ^ row: 8 distinct bank groups per quarter-warp.
-    // bf16 grad_y keeps the direct global loads (LDG.64 of 4 positions, next stage in flight during the wait).
+    // bf16 grad_y: the same with 64-byte box rows, 64-byte swizzle and LDS.64 (see the load loop below).
     const int pw = warp - 8;
     // a quarter-warp = 2 position groups x 4 planes: 8 distinct 16-byte bank groups.  bf16 grad_y: the position groups
     // of a half-warp are {0,1,4,5} / {2,3,6,7}, so that the LDS.64 of a half-warp cover all four 16-byte chunks
