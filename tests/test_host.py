@@ -145,3 +145,22 @@ def test_allreduce_filter_grads_world_size_2_gloo():
             lo, bd = out[r]
             assert torch.equal(lo, torch.full((6, 1), 3.0))
             assert torch.equal(bd, torch.arange(6.0).view(6, 1))
+
+
+def test_bench_reference_arm_runs_on_cpu_and_ours_refuses_without_a_gpu():
+    """`bench.py --impl reference` (the oracle port timed on the host cores) prints the contract's JSON line; our own
+    arm has no CPU fallback and must say so instead of printing a number."""
+    import json
+    import subprocess
+    import sys
+    bench = os.path.join(ROOT, "bench.py")
+    p = subprocess.run([sys.executable, bench, "--impl", "reference", "--workload", "cfg1_b1_t16000_fwd", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "audio-s/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    if not torch.cuda.is_available():
+        q = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+        assert q.returncode != 0 and "no CPU fallback" in (q.stdout + q.stderr)
+        assert not [l for l in q.stdout.splitlines() if l.startswith("{")]
