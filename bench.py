@@ -1,17 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- SincConv fwd+bwd throughput in audio-seconds/second (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|fma|tc]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--engine auto|fma|tc|tc_tf32]
 
 One "step" = one forward + backward (grad-input + parameter grads) of the SincConv hot path over one batch of
 synthetic waveforms.  Workload per rank: BASELINE config[1] -- batch 32 x 3 s @ 16 kHz (48 000 samples), fp32,
 C=64 filters, K=251 taps; with N ranks the global batch is 32*N (weak scaling) and the 2*C-float parameter
 gradient is all-reduced over NCCL every step.  audio-seconds = B*T/16000.
 
-Prints ONE JSON line (rank 0).  Keys beyond the base contract: `roofline` (dominant kernel, measured live with
-CUDA events around direct C-ABI launches), `kernels` (all three), `cpu_baseline` (the oracle port of the
-reference's CPU torch path on this box's host cores), `e2e` (module API with pinned host input, H2D + D2H inside
-the timed region), `clocks`, `gpu_launches`.
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline       dominant kernel, timed live with CUDA events around direct C-ABI launches; `frac` is against the
+                 split-adjusted tensor ceiling (measured bf16 dense rate / MMAs per algorithmic product),
+                 `frac_of_raw_bf16` against the measured bf16 dense rate itself
+  kernels        all three kernels
+  sustained      the same step, >= 2000 back to back (the SM clock settles lower than in the short burst)
+  gpu_reference  the reference's own torch ops (synthesis + F.conv1d, autograd backward) through cuDNN on this GPU,
+                 TF32 on and off -- the practical GPU bar
+  cfg4 / cfg5    BASELINE configs 4 and 5 as specified: global 1024 x 48 000 fp32 resp. 64 x 960 000 bf16, rows
+                 [r*G/N, (r+1)*G/N) on rank r (strong scaling), per-row seeds, in-backward all-reduce; cfg4 asserts
+                 that every rank's parameter gradients equal the single-GPU result to 1e-5
+  cpu_baseline   the reference's CPU torch path on this box's host cores (the staged reference module when
+                 baseline/_ref holds it -- kind "reference" -- else the oracle port)
+  e2e            module API with pinned host input: H2D and D2H on two copy streams inside the timed region
+  clocks, gpu_launches
 """
 from __future__ import annotations
 
@@ -35,6 +46,8 @@ C, K = 64, 251
 FLOP_FWD = 2 * C * K            # per input sample
 FLOP_PER_SAMPLE = 3 * FLOP_FWD  # fwd + grad-filter + grad-input = 96 384
 BYTES_PER_SAMPLE_F32 = 524      # fwd 4+256, bwd 256+4+4
+BYTES_PER_SAMPLE_BF16 = 268
+ROUND = "r02"
 
 WORKLOADS = {
     # name: (B per rank, T, out dtype, sample_rate of the module, needs input grad)
@@ -43,6 +56,16 @@ WORKLOADS = {
     "cfg4_b128_t48000_fp32": (128, 48000, "fp32", 16000, True),
     "cfg5_b8_t960000_bf16": (8, 960000, "bf16", 16000, True),
 }
+
+
+def workload_config(name, world):
+    """`config` of the JSON line: names the workload, identical for both arms (the driver compares them)."""
+    B, T, dt, sr, need_x = WORKLOADS[name]
+    return {"workload": name, "batch_per_gpu": B, "global_batch": B * world, "samples": T, "filters": C, "taps": K,
+            "module_sample_rate": sr, "activations": dt, "grads": "input + low_hz_/band_hz_",
+            "exchange": "allreduce(2*C fp32) over NCCL inside backward, overlapped with grad-input" if world > 1 else "none",
+            "l2_policy": f"activations ({B * C * T * (4 if dt == 'fp32' else 2) / 1e6:.0f} MB y, the same of grad_y per step) "
+                         "exceed the 126 MB L2"}
 
 
 def load_peaks():
@@ -127,14 +150,57 @@ def dist_env():
     return rank, local, world
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers are allocated
+    (first touch) next to its PCIe root: at 8 ranks the host link is shared and remote-node buffers cost bandwidth."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if not out:
+            return None
+        bus = out[-12:] if len(out) >= 12 else out          # 00000000:1b:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference's CPU torch path
+# reference arm / cpu baseline: the reference's own CPU torch path
 # ------------------------------------------------------------------------------------------------------
-def cpu_oracle_step_fn(B, T, sr):
+def reference_module_class():
+    """(class, kind): the REAL agents.perception.SincConv1d from the staged copy under baseline/_ref (kind
+    "reference"; staged by oracle/stage_reference.py) or the oracle port (kind "port": same torch ops, same order,
+    pinned bit-identical to the reference by oracle/pin_against_reference.py)."""
+    staged = os.path.join(ROOT, "baseline", "_ref", "reference")
+    if os.path.exists(os.path.join(staged, "agents", "perception.py")):
+        try:
+            sys.path.insert(0, staged)
+            from agents.perception import SincConv1d as RefSinc
+            return RefSinc, "reference"
+        except Exception:
+            sys.path.remove(staged)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import sinc_oracle as O
+    return O.OracleSincConv1d, "port"
+
+
+def cpu_reference_step_fn(B, T, sr):
+    cls, kind = reference_module_class()
     torch.set_num_threads(os.cpu_count() or 1)
-    m = O.OracleSincConv1d(C, K, sample_rate=sr)
+    m = cls(C, K, sample_rate=sr)
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(B, 1, T, generator=gen)
     g = torch.randn(B, C, T, generator=gen)
@@ -146,7 +212,7 @@ def cpu_oracle_step_fn(B, T, sr):
         y = m(xr)
         y.backward(g)
         return float(m.low_hz_.grad.sum())
-    return step
+    return step, kind
 
 
 def time_cpu(step, reps, warm=1):
@@ -166,20 +232,22 @@ def run_reference(args):
         return
     B, T, dt, sr, _ = WORKLOADS[args.workload]
     Bs = min(B, 32)
-    step = cpu_oracle_step_fn(Bs, T, sr)
+    step, kind = cpu_reference_step_fn(Bs, T, sr)
     ts = time_cpu(step, args.steps, warm=min(args.warmup, 2))
     total = sum(ts)
     audio = Bs * T / SR_AUDIO
     value = audio * len(ts) / total
     cores = torch.get_num_threads()
+    what = ("the unmodified agents.perception.SincConv1d staged under baseline/_ref" if kind == "reference"
+            else "oracle port of the reference CPU torch path (same torch ops in the same order)")
     line = {
         "impl": "reference", "metric": "sincconv_fwd_bwd_audio_seconds_per_second", "value": value,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_step": Bs, "samples": T, "filters": C, "taps": K,
-                   "note": "reference CPU torch path (oracle port: same torch ops in the same order), all host threads"},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+        "dtype": "f32" if dt == "fp32" else "f32 math, bf16 activations", "data": "synthetic",
+        "config": workload_config(args.workload, world),
+        "note": f"{what}; CPU torch, all host threads; rank 0 only, one bounded sample of the workload per step",
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": kind,
                          "sample": f"B={Bs} x T={T} fwd+bwd (param + input grads), {len(ts)} steps"},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -198,6 +266,7 @@ def run_ours(args):
     rank, local, world = dist_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the SincConv path has no CPU fallback")
+    numa = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -223,13 +292,17 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_resident():
-        xr = x.detach().requires_grad_(need_x)
-        m.low_hz_.grad = None
-        m.band_hz_.grad = None
-        y = m(xr)
-        y.backward(g)
-        return xr.grad
+    def make_step(mod, xs, gs, want_x):
+        def step():
+            xr = xs.detach().requires_grad_(want_x)
+            mod.low_hz_.grad = None
+            mod.band_hz_.grad = None
+            y = mod(xr)
+            y.backward(gs)
+            return xr.grad
+        return step
+
+    step_resident = make_step(m, x, g, need_x)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -248,46 +321,56 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    def in_kernel_clocks(mod, fn):
+        """nvidia-smi reports the clock the driver ASKS for; under the combined tensor + HBM load of this path the SMs
+        run slower (power management).  One more step with the diagnostic time stamps switched on (per-call option of
+        the C ABI): the kernels stamp the SM cycle counter and the nanosecond timer at entry and exit (CTA 0);
+        cycles / ns is the clock they really ran at."""
+        try:
+            with mod.capture(phase_stamps=True) as rec:
+                fn()
+                torch.cuda.synchronize()
+            st = rec["phase_stamps"].cpu().tolist()
+            real = {}
+            for k, name in enumerate(("fwd", "bwd_input", "bwd_filter")):
+                c0, t0, c2, t2 = st[6 * k], st[6 * k + 1], st[6 * k + 4], st[6 * k + 5]
+                if t2 > t0 and c2 > c0:
+                    real[name] = round((c2 - c0) / ((t2 - t0) / 1e3), 1)
+            return real or None
+        except Exception:
+            return None
+
     # --- headline: whole step, inputs resident in HBM --------------------------------------------------
     with ClockSampler(local) as clk:
         n0 = sb.kernel_launch_count()
         ms_total = timed(step_resident, args.steps, args.warmup)
         launches = (sb.kernel_launch_count() - n0) * args.steps // (args.steps + args.warmup)
+        real = in_kernel_clocks(m, step_resident)
     clocks = clk.summary()
-    # nvidia-smi reports the clock the driver ASKS for; under the combined tensor + HBM load of this path the SMs run
-    # slower (power management).  The kernels stamp the SM cycle counter and the nanosecond timer at entry and exit
-    # (CTA 0, last launch of the timed region): cycles / ns is the clock they really ran at.
-    try:
-        stamps = (ctypes.c_longlong * 20)()
-        if lib.sinc_tc_phase_stamps(stamps) == 0:
-            real = {}
-            for k, name in enumerate(("fwd", "bwd_input", "bwd_filter")):
-                c0, t0, c2, t2 = stamps[6 * k], stamps[6 * k + 1], stamps[6 * k + 4], stamps[6 * k + 5]
-                if t2 > t0 and c2 > c0:
-                    real[name] = round((c2 - c0) / ((t2 - t0) / 1e3), 1)
-            if real:
-                clocks["sm_mhz_in_kernel"] = real
-    except Exception:
-        pass
+    if real:
+        clocks["sm_mhz_in_kernel"] = real
     ms_step = ms_total / args.steps
     value = world * audio_per_step / (ms_step * 1e-3)
 
     # --- e2e: module API, pinned host input -> H2D, D2H of grad-input and parameter grads ---------------
-    # A training loop's input pipeline: the H2D copy of step k+1 and the D2H read-back of step k-1 run on a
-    # copy stream while step k computes (two device buffers); every byte still moves inside the timed region.
+    # A training loop's input pipeline: the H2D copy of step k+1 and the D2H read-back of step k-1 run while step k
+    # computes -- on TWO copy streams (the GPU has separate copy engines per direction; one stream would serialise the
+    # two directions, which is what limited the 8-rank number when eight ranks share the host link).  Every byte still
+    # moves inside the timed region.
     gx_host = torch.empty(B, 1, T).pin_memory()
     gp_host = torch.empty(2, C, 1).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
+    h2d_stream = torch.cuda.Stream(device=dev)
+    d2h_stream = torch.cuda.Stream(device=dev)
     xdev = [torch.empty(B, 1, T, device=dev) for _ in range(2)]
     h2d_done = [torch.cuda.Event() for _ in range(2)]
     buf_free = [torch.cuda.Event() for _ in range(2)]
     state = {"k": 0, "primed": False}
 
     def issue_h2d(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(buf_free[slot])
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(buf_free[slot])      # the step that used this buffer has finished with it
             xdev[slot].copy_(x_host, non_blocking=True)
-            h2d_done[slot].record(copy_stream)
+            h2d_done[slot].record(h2d_stream)
 
     def step_e2e():
         main = torch.cuda.current_stream(dev)
@@ -305,20 +388,20 @@ def run_ours(args):
         m.band_hz_.grad = None
         y = m(xd)
         y.backward(g)
+        buf_free[slot].record(main)              # backward has consumed the waveform buffer
         done = torch.cuda.Event()
         done.record(main)
         gxd = xd.grad if need_x else None
         glow, gband = m.low_hz_.grad, m.band_hz_.grad
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done)
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(done)
             if need_x:
                 gx_host.copy_(gxd, non_blocking=True)
-                gxd.record_stream(copy_stream)
+                gxd.record_stream(d2h_stream)
             gp_host[0].copy_(glow, non_blocking=True)
             gp_host[1].copy_(gband, non_blocking=True)
-            glow.record_stream(copy_stream)
-            gband.record_stream(copy_stream)
-            buf_free[slot].record(copy_stream)
+            glow.record_stream(d2h_stream)
+            gband.record_stream(d2h_stream)
         xdev[slot].requires_grad_(False)
         xdev[slot].grad = None
         state["k"] = k + 1
@@ -331,7 +414,8 @@ def run_ours(args):
         e0.record()
         for _ in range(steps):
             step_e2e()
-        torch.cuda.current_stream(dev).wait_stream(copy_stream)   # the last read-back is part of the region
+        torch.cuda.current_stream(dev).wait_stream(d2h_stream)   # the last read-back is part of the region
+        torch.cuda.current_stream(dev).wait_stream(h2d_stream)
         e1.record()
         sync_all()
         ms = e0.elapsed_time(e1)
@@ -347,7 +431,7 @@ def run_ours(args):
     ms_e2e = min(e2e_runs)
     e2e_value = world * audio_per_step / (ms_e2e * 1e-3)
 
-    def copy_gbs(dst, src, reps=5):      # the host link on its own, for context (pinned memory, copy stream idle)
+    def copy_gbs(dst, src, reps=5):      # the host link on its own, for context (pinned memory, copy streams idle)
         torch.cuda.synchronize()
         best = None
         for _ in range(reps):
@@ -359,7 +443,7 @@ def run_ours(args):
             t = e0.elapsed_time(e1)
             best = t if best is None or t < best else best
         return src.numel() * src.element_size() / best / 1e6
-    link = {"h2d_gbs": copy_gbs(xdev[0], x_host), "d2h_gbs": copy_gbs(gx_host, xdev[0])}
+    link = {"h2d_gbs": copy_gbs(xdev[0], x_host), "d2h_gbs": copy_gbs(gx_host, xdev[0]), "numa_node": numa}
     h2d = x_host.numel() * 4
     d2h = (gx_host.numel() * 4 if need_x else 0) + gp_host.numel() * 4
 
@@ -368,18 +452,89 @@ def run_ours(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if dt == "fp32" else "f32 math, bf16 activations", "data": "synthetic",
-        "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * world, "samples": T,
-                   "filters": C, "taps": K, "module_sample_rate": sr, "engine": args.engine,
-                   "grads": "input + low_hz_/band_hz_", "exchange": "allreduce(2*C fp32) over NCCL inside backward, overlapped with grad-input" if world > 1 else "none",
-                   "l2_policy": "activations (393 MB y, 393 MB grad_y per step) exceed the 126 MB L2"},
+        "config": workload_config(args.workload, world),
+        "engine": args.engine,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e, "ms_per_step_runs": e2e_runs,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": link,
                 "note": "nn.Module API; every step copies its waveforms from pinned host memory and reads grad-input + parameter "
-                        "grads back to pinned host memory (copy stream, double-buffered: copies overlap the neighbouring "
-                        "steps' compute); grad_y resident (produced on-device by the next layer)"},
+                        "grads back to pinned host memory (one copy stream per direction, double-buffered: copies overlap the "
+                        "neighbouring steps' compute); grad_y resident (produced on-device by the next layer)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+
+    # --- sustained: the same step >= 2000 times back to back (the SM clock settles under tensor + HBM load) ---------
+    if args.sustained > 0:
+        ms_sus = timed(step_resident, args.sustained, 3) / args.sustained
+        rec = {"steps": args.sustained, "ms_per_step": ms_sus, "value": world * audio_per_step / (ms_sus * 1e-3),
+               "unit": "audio-s/s", "vs_burst": ms_step / ms_sus}
+        real = in_kernel_clocks(m, step_resident)
+        if real:
+            rec["sm_mhz_in_kernel"] = real
+        line["sustained"] = rec
+
+    # --- BASELINE configs 4 and 5 as specified (strong scaling over the N ranks of this run) -------------------------
+    if args.workload == "cfg2_b32_t48000_fp32" and not args.no_sub:
+        from sincformer_metacog_speech_enhancement_b200 import shard_rows
+
+        def rows_on_device(r0, r1, Tn, dtype, what):
+            """per-row seeds: row i of the GLOBAL batch is randn(seed = 2*i [+1 for grad_y]) whatever the sharding"""
+            if what == "x":
+                out = torch.empty(r1 - r0, 1, Tn, device=dev)
+            else:
+                out = torch.empty(r1 - r0, C, Tn, device=dev, dtype=dtype)
+            gg = torch.Generator(device=dev)
+            for i in range(r0, r1):
+                gg.manual_seed(2 * i + (0 if what == "x" else 1))
+                if what == "x":
+                    out[i - r0] = torch.randn(1, Tn, device=dev, generator=gg)
+                else:
+                    out[i - r0] = torch.randn(C, Tn, device=dev, generator=gg).to(dtype)
+            return out
+
+        def strong(name, G, Tn, dtype, check):
+            r0, r1 = shard_rows(G, rank, world)
+            mm = sb.SincConv1d(C, K, sample_rate=16000, out_dtype=dtype).to(dev)
+            if world > 1:
+                mm.enable_grad_sync()
+            xs = rows_on_device(r0, r1, Tn, dtype, "x")
+            gs = rows_on_device(r0, r1, Tn, dtype, "g")
+            fn = make_step(mm, xs, gs, True)
+            steps = max(3, min(args.steps, 10))
+            ms = timed(fn, steps, 3) / steps
+            rec = {"global_batch": G, "samples": Tn, "rows_per_rank": r1 - r0, "activations": "bf16" if dtype == torch.bfloat16 else "fp32",
+                   "scaling": "strong", "steps": steps, "ms_per_step": ms, "value": G * Tn / SR_AUDIO / (ms * 1e-3), "unit": "audio-s/s"}
+            if check:
+                # every rank's (all-reduced) parameter gradients against the SINGLE-GPU result: rank 0 runs the whole
+                # global batch alone (no exchange), broadcasts, each rank compares, the worst error is reported
+                mine = torch.cat([mm.low_hz_.grad.reshape(-1), mm.band_hz_.grad.reshape(-1)]).double()
+                if world > 1:
+                    ref = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+                    if rank == 0:
+                        del xs, gs
+                        m1 = sb.SincConv1d(C, K, sample_rate=16000, out_dtype=dtype).to(dev)
+                        xa = rows_on_device(0, G, Tn, dtype, "x")
+                        ga = rows_on_device(0, G, Tn, dtype, "g")
+                        make_step(m1, xa, ga, True)()
+                        ref = torch.cat([m1.low_hz_.grad.reshape(-1), m1.band_hz_.grad.reshape(-1)]).double()
+                        del xa, ga
+                    dist.broadcast(ref, src=0)
+                    err = torch.stack([((mine[:C] - ref[:C]).abs().max() / ref[:C].abs().max()),
+                                       ((mine[C:] - ref[C:]).abs().max() / ref[C:].abs().max())]).max().reshape(1)
+                    dist.all_reduce(err, op=dist.ReduceOp.MAX)
+                    rec["param_grads_vs_single_gpu"] = float(err.item())
+                    rec["check"] = "all ranks equal the N=1 result to 1e-5" if err.item() <= 1e-5 else "FAILED"
+                    if err.item() > 1e-5:
+                        raise SystemExit(f"bench.py: {name}: sharded parameter gradients differ from the single-GPU result "
+                                         f"by {err.item():.3e} (> 1e-5)")
+                else:
+                    rec["check"] = "N = 1: this run IS the single-GPU result"
+            return rec
+
+        line["cfg4"] = strong("cfg4", 1024, 48000, torch.float32, True)
+        torch.cuda.empty_cache()
+        line["cfg5"] = strong("cfg5", 64, 960000, torch.bfloat16, False)
+        torch.cuda.empty_cache()
 
     # --- per-kernel timings through the C ABI (rank 0, N == 1 only) -------------------------------------
     if rank == 0 and world == 1:
@@ -392,17 +547,22 @@ def run_ours(args):
         code = _lib.DTYPE_BF16 if dt == "bf16" else _lib.DTYPE_F32
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        used = ctypes.c_int32(0)
+        opt = _lib.Options()
+        opt.engine = _lib.ENGINE_CODES[args.engine]
+        opt.engines_used = ctypes.pointer(used)
+        O = ctypes.byref(opt)
 
         def k_fwd():
-            _lib.check(lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), code, B, T, P(ws), nbytes, stream), "fwd")
+            _lib.check(lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), code, B, T, P(ws), nbytes, stream, O), "fwd")
 
         def k_bwd_input():
             _lib.check(lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), code, P(gx), None, None, None, B, T,
-                                         P(ws), nbytes, stream), "bwd_input")
+                                         P(ws), nbytes, stream, O), "bwd_input")
 
         def k_bwd_filter():
             _lib.check(lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), code, None, P(gp[0]), P(gp[1]), None, B, T,
-                                         P(ws), nbytes, stream), "bwd_filter")
+                                         P(ws), nbytes, stream, O), "bwd_filter")
 
         esize = 2 if dt == "bf16" else 4
         n = B * T
@@ -412,56 +572,93 @@ def run_ours(args):
                 ("bwd_input", k_bwd_input, FLOP_FWD * n, n * (C * esize + 4)),
                 ("bwd_filter+finalize", k_bwd_filter, FLOP_FWD * n, n * (C * esize + 4))):
             ms = timed(fn, max(3, args.steps // 2), 3) / max(3, args.steps // 2)
-            mask = lib.sinc_last_engine_mask()
-            tc_bit, h16_bit = {"fwd": (1, 8), "bwd_input": (2, 16)}.get(name, (4, 32))
-            eng = "fma" if not (mask & tc_bit) else ("tc16" if (mask & h16_bit) else "tc_tf32")
+            eng = _lib.decode_engines(used.value)[{"bwd_filter+finalize": "bwd_filter"}.get(name, name)]
             kern[name] = {"ms": ms, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6, "engine": eng}
         line["kernels"] = kern
         dom = max(kern, key=lambda k: kern[k]["ms"])
         # Roofline of the dominant kernel.  The contraction is compute-bound on every pipe (184 FLOP/B).
         # FMA engine: FP32 pipe, nominal 148 SM x 128 lanes x 2 x clocks.max.sm (not in MEASURED_PEAKS).
-        # tcgen05 engines: every algorithmic product costs three MMAs (hi*hi + hi*lo + lo*hi), so the ceiling for
-        # ALGORITHMIC flops is the measured dense bf16 rate / 3 (kind::f16 operands: fp16 or bf16 split) or
-        # / 2 / 3 (kind::tf32 operands).
+        # tcgen05 engines: an algorithmic product costs `mmas` tensor-core instructions -- 3 with fp32 activations
+        # (hi*hi + hi*lo + lo*hi); 2 in the backward kernels with bf16 activations (grad_y is exact in one bf16 piece);
+        # the forward always splits both operands (3) -- so the ceiling for ALGORITHMIC flops is the measured dense
+        # bf16 rate / mmas (kind::f16 operands) or / 2 / 3 (kind::tf32 operands).  `frac_of_raw_bf16` is the same
+        # achieved number against the measured dense bf16 rate itself.
         sm_max = clocks.get("sm_max_mhz") or 1965.0
 
-        def peak_of(eng):
+        def peak_of(name, eng):
             if eng == "tc16":
-                return peaks["bf16_tflops"] / 3, "tensor", (f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / 3 "
-                                                           "(16-bit split operands: three kind::f16 MMAs per product)")
+                mmas = 2 if (dt == "bf16" and name != "fwd") else 3
+                return peaks["bf16_tflops"] / mmas, "tensor", (
+                    f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / {mmas} (16-bit split operands: "
+                    f"{mmas} kind::f16 MMAs per algorithmic product)")
             if eng == "tc_tf32":
                 return peaks["bf16_tflops"] / 2 / 3, "tensor", (f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / 2 (tf32) "
                                                                "/ 3 (3xTF32 split)")
             return 148 * 128 * 2 * sm_max * 1e6 / 1e12, "fp32_fma", (f"nominal 148 SM x 128 FMA lanes x 2 x {sm_max:.0f} MHz "
                                                                      "(FP32 pipe is not in MEASURED_PEAKS)")
         for k in kern:
-            kern[k]["frac_of_pipe_peak"] = kern[k]["tflops"] / peak_of(kern[k]["engine"])[0]
-        peak, bound, peak_src = peak_of(kern[dom]["engine"])
+            kern[k]["frac_of_pipe_peak"] = kern[k]["tflops"] / peak_of(k, kern[k]["engine"])[0]
+            kern[k]["frac_of_raw_bf16"] = kern[k]["tflops"] / peaks["bf16_tflops"]
+        peak, bound, peak_src = peak_of(dom, kern[dom]["engine"])
         # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py)
         traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fh:
-                tr = json.load(fh)
-            kname = {"fwd": "fwd", "bwd_input": "bwd_input", "bwd_filter+finalize": "bwd_filter"}[dom] + \
-                    {"tc16": "_tc16_kernel", "tc_tf32": "_tc_kernel", "fma": "_fma_kernel"}[kern[dom]["engine"]]
-            if args.workload == "cfg2_b32_t48000_fp32" and kname in tr:
-                traffic = tr[kname]["dram_bytes"]
-        except Exception:
-            traffic = None
+        for rnd in (ROUND, "r01"):
+            try:
+                with open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json")) as fh:
+                    tr = json.load(fh)
+                kname = {"fwd": "fwd", "bwd_input": "bwd_input", "bwd_filter+finalize": "bwd_filter"}[dom] + \
+                        {"tc16": "_tc16_kernel", "tc_tf32": "_tc_kernel", "fma": "_fma_kernel"}[kern[dom]["engine"]]
+                if args.workload == "cfg2_b32_t48000_fp32" and kname in tr:
+                    traffic = tr[kname]["dram_bytes"]
+                    break
+            except Exception:
+                continue
+        alg_flops = FLOP_PER_SAMPLE * n / ms_step / 1e9
         line["roofline"] = {"kernel": dom, "bound": bound, "achieved": kern[dom]["tflops"], "peak": peak,
-                            "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak, "traffic": traffic,
+                            "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak,
+                            "frac_of_raw_bf16": kern[dom]["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
                             "peak_source": peak_src,
                             "hbm": {"achieved_gbs": kern[dom]["gbs"], "peak_gbs": peaks["hbm_gbs"],
                                     "frac": kern[dom]["gbs"] / peaks["hbm_gbs"]},
-                            "step": {"algorithmic_tflops": FLOP_PER_SAMPLE * n / ms_step / 1e9,
-                                     "algorithmic_gbs": (BYTES_PER_SAMPLE_F32 if dt == "fp32" else 268) * n / ms_step / 1e6}}
+                            "step": {"algorithmic_tflops": alg_flops,
+                                     "frac_of_split_adjusted_burst": alg_flops / (peaks["bf16_tflops"] / 3),
+                                     "frac_of_split_adjusted_sustained": alg_flops / (peaks["bf16_tflops_sustained"] / 3),
+                                     "frac_of_raw_bf16": alg_flops / peaks["bf16_tflops"],
+                                     "algorithmic_gbs": (BYTES_PER_SAMPLE_F32 if dt == "fp32" else BYTES_PER_SAMPLE_BF16) * n / ms_step / 1e6}}
+
+        # --- gpu_reference: the reference's own torch ops through cuDNN on this GPU (the practical GPU bar) ---------
+        if not args.no_gpu_ref and dt == "fp32":
+            try:
+                cls, kind = reference_module_class()
+                rm = cls(C, K, sample_rate=sr).to(dev)
+                gref = g.float()
+
+                def ref_step():
+                    xr = x.detach().requires_grad_(need_x)
+                    for p in rm.parameters():
+                        p.grad = None
+                    rm(xr).backward(gref)
+                rec = {"kind": kind, "what": "unmodified synthesis + F.conv1d + autograd backward via torch/cuDNN on this GPU, same batch"}
+                prev = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+                for label, flag in (("tf32", True), ("fp32", False)):
+                    torch.backends.cudnn.allow_tf32 = flag
+                    torch.backends.cuda.matmul.allow_tf32 = flag
+                    ms = timed(ref_step, 5, 3) / 5
+                    rec[label] = {"ms_per_step": ms, "value": audio_per_step / (ms * 1e-3)}
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+                rec["speedup_vs_fp32"] = rec["fp32"]["ms_per_step"] / ms_step
+                line["gpu_reference"] = rec
+                del rm
+            except Exception as e:   # a baseline leg must never take the bench down
+                line["gpu_reference"] = {"unavailable": repr(e)[:200]}
+
         if not args.no_cpu:
             Bs = min(B, 32)
-            step = cpu_oracle_step_fn(Bs, T, sr)
+            step, kind = cpu_reference_step_fn(Bs, T, sr)
             ts = time_cpu(step, 3, warm=1)
             line["cpu_baseline"] = {"value": Bs * T / SR_AUDIO / min(ts), "unit": "audio-s/s",
-                                    "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"oracle port of the reference CPU torch path, B={Bs} x T={T} fwd+bwd, best of 3"}
+                                    "cores": torch.get_num_threads(), "kind": kind,
+                                    "sample": f"reference CPU torch path ({kind}), B={Bs} x T={T} fwd+bwd, best of 3"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -476,7 +673,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--engine", default="auto", choices=["auto", "fma", "tc", "tc_tf32"])
     ap.add_argument("--workload", default="cfg2_b32_t48000_fp32", choices=sorted(WORKLOADS))
+    ap.add_argument("--sustained", type=int, default=2000, help="steps of the back-to-back `sustained` record (0 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-gpu-ref", action="store_true", help="skip the torch/cuDNN gpu_reference leg")
+    ap.add_argument("--no-sub", action="store_true", help="skip the cfg4 / cfg5 strong-scaling sub-records")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -16,6 +16,8 @@
  *     caller must preserve: besides scratch it holds a self-validating copy of the synthesised
  *     filters (written by a parameter-gradient call, used by a later grad-input call only if its
  *     header matches that call's filter bank word for word and its checksums hold);
+ *   - the library has no mutable process-wide state (per-call options instead: sinc_options) apart from immutable
+ *     per-device caches (SM count, the driver entry point of cuTensorMapEncodeTiled) and a launch counter;
  *   - return value: 0 = success, < 0 = argument error (SINC_E_*), > 0 = a cudaError_t;
  *     sinc_strerror() turns either into text.  Nothing throws or exits across this boundary;
  *   - C = out_channels, K = kernel_size (odd; the reference bumps even K to K+1 in __init__,
@@ -34,15 +36,15 @@
 extern "C" {
 #endif
 
-#define SINC_ABI_VERSION 1
+#define SINC_ABI_VERSION 2
 
 #define SINC_DTYPE_F32 0
 #define SINC_DTYPE_BF16 1
 
-/* kernel-family selector for sinc_set_engine(): 0 = pick the fastest supported for the shape
- * (default), 1 = FP32 FMA kernels only, 2 = tcgen05 tensor-core kernels only (16-bit split operands where a
- * kernel for the shape exists, else 3xTF32; error if neither supports the shape), 3 = tcgen05 with the
- * 3xTF32 split in every pass.  Every engine is hand-written sm_100a CUDA; there is no CPU path. */
+/* kernel-family selector (sinc_options.engine): 0 = pick the fastest supported for the shape (default), 1 = FP32 FMA
+ * kernels only, 2 = tcgen05 tensor-core kernels only (16-bit split operands where a kernel for the shape exists, else
+ * 3xTF32; error if neither supports the shape), 3 = tcgen05 with the 3xTF32 split in every pass.  Every engine is
+ * hand-written sm_100a CUDA; there is no CPU path. */
 #define SINC_ENGINE_AUTO 0
 #define SINC_ENGINE_FMA 1
 #define SINC_ENGINE_TC 2
@@ -76,21 +78,29 @@ typedef struct sinc_filterbank {
 int sinc_abi_version(void);
 const char* sinc_strerror(int code);
 
-/* Number of kernels this library has launched in this process (monotonic; for bench accounting). */
+/* Number of kernels this library has launched in this process (monotonic counter; for bench accounting). */
 uint64_t sinc_kernel_launch_count(void);
 
-/* Select the kernel family for subsequent calls from this process (SINC_ENGINE_*). */
-int sinc_set_engine(int engine);
-int sinc_get_engine(void);
-/* Data-parallel use: the grad-input kernel is persistent (one CTA per SM, all of its shared memory and registers), so a
- * collective launched next to it cannot start until it ends.  With n > 0 that kernel leaves n SMs free (process-wide,
- * 0..64, default 0); the host mirror sets it around the grad-input launch when the parameter-gradient all-reduce
- * is in flight.  No counterpart in the reference (single process). */
-int sinc_set_reserved_sms(int n);
-/* Which engine the last successful sinc_forward / sinc_backward call of this process actually used:
- * bit 0 forward, bit 1 grad-input, bit 2 grad-filter; a set bit means tcgen05, clear means FMA.
- * Bits 3/4/5 (forward / grad-input / grad-filter): the tcgen05 kernel used 16-bit split operands. */
-int sinc_last_engine_mask(void);
+/* Per-call options of sinc_forward / sinc_backward (NULL = all defaults).  The library keeps NO mutable state between
+ * calls: everything that used to be a process-wide setting travels with the call, so two modules on two devices or
+ * threads cannot disturb each other.  No counterpart in the reference (single process, one engine).
+ *   engine        SINC_ENGINE_*
+ *   reserved_sms  data-parallel use: the persistent grad-input kernel (one CTA per SM, all of its shared memory and
+ *                 registers) leaves this many SMs free (0..64), so that a collective launched next to it -- the
+ *                 parameter-gradient all-reduce in flight -- can start before it ends
+ *   engines_used  optional HOST int: receives which engine each pass of THIS call used -- bit 0 forward, bit 1
+ *                 grad-input, bit 2 grad-filter: set = tcgen05, clear = FMA; bits 3/4/5 (same order): the tcgen05
+ *                 kernel used 16-bit split operands
+ *   phase_stamps  optional DEVICE buffer of 20 int64 (diagnostic, written by CTA 0 of each 16-bit tcgen05 kernel):
+ *                 out[6*k + ...] = {SM cycle counter, nanosecond timer} at kernel entry, after the prologue and at
+ *                 exit, for k = 0 forward, 1 grad-input, 2 grad-filter (cycles / ns = the SM clock the kernel really
+ *                 ran at); out[18] = 1 if the grad-input launch took its filters from the workspace table */
+typedef struct sinc_options {
+  int32_t engine;
+  int32_t reserved_sms;
+  int32_t* engines_used;
+  long long* phase_stamps;
+} sinc_options;
 
 /* Bytes of device scratch sinc_forward / sinc_backward need for this shape (never 0). */
 size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K);
@@ -106,7 +116,7 @@ int sinc_synthesize(const sinc_filterbank* fb, float* filters_out, void* stream)
  * padding=K//2).  y_dtype selects fp32 or bf16 storage of y (math is fp32 either way). */
 int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, void* y,
                  int32_t y_dtype, int64_t B, int64_t T, void* workspace, size_t workspace_bytes,
-                 void* stream);
+                 void* stream, const sinc_options* opts);
 
 /* Backward of sinc_forward.
  * Replaces autograd's ConvolutionBackward0 of agents/perception.py:117-118 (grad-input, grad-filter)
@@ -120,11 +130,11 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
 int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, const void* grad_y,
                   int32_t gy_dtype, float* grad_x, float* grad_low, float* grad_band,
                   float* grad_filters, int64_t B, int64_t T, void* workspace,
-                  size_t workspace_bytes, void* stream);
+                  size_t workspace_bytes, void* stream, const sinc_options* opts);
 
 /* ---- next row N1: the GroupNorm(8, C) + GELU that follows the layer -----------------
  * Replaces agents/perception.py:233-234 (the GroupNorm module `sinc_norm` = nn.GroupNorm(8, C) of :157 applied to
- * the layer output, then F.gelu) with streaming kernels that touch the (B,C,T) activation as few times as possible.  fp32, T % 4 == 0,
+ * the layer output, then F.gelu) with streaming kernels that touch the (B,C,T) activation as few times as possible.  fp32; any T
  * 16-byte aligned tensors.
  *
  * sinc_forward_gn: sinc_forward (fp32 y) that also emits, from the convolution epilogue, the partial sums the
@@ -139,7 +149,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
  *   float2 scratch [B*C][sinc_gn_chunks(T)]. */
 int64_t sinc_forward_gn_partials(int64_t T);
 int sinc_forward_gn(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, float* y, int64_t B, int64_t T,
-                    float* gn_partial, void* stream);
+                    float* gn_partial, void* stream, const sinc_options* opts);
 int sinc_gn_chunks(int64_t T);
 int sinc_gn_stats(const float* y, int64_t B, int64_t T, int32_t C, float* partial, void* stream);
 int sinc_gn_gelu_forward(const float* y, const float* partial, int32_t np, int32_t rows_per_group, const float* gamma,
@@ -149,42 +159,11 @@ int sinc_gn_gelu_backward(const float* dz, const float* y, const float* stats, c
                           float* dy, float* dgamma, float* dbeta, float* partial, int64_t B, int64_t T, int32_t C,
                           int32_t G, void* stream);
 
-/* Diagnostic: *status_host = 1 if any tcgen05 kernel of this process gave up waiting on one of its internal
- * barriers (a protocol bug; results are then invalid).  Synchronises the device. */
-int sinc_tc_status(int* status_host);
-
-/* Diagnostic: time stamps of the LAST launch of each 16-bit tcgen05 kernel, taken by CTA 0: out20[6*k + ...] =
- * {SM cycle counter, nanosecond timer} at kernel entry, after the prologue (filter synthesis, operand set-up) and
- * at exit, for k = 0 forward, 1 grad-input, 2 grad-filter.  cycles / ns = the SM clock the kernel really ran at.
- * out20[18] = 1 if that grad-input launch took its filters from the table the grad-filter kernel leaves in the
- * workspace, 0 if it synthesised them.  Synchronises the device. */
-int sinc_tc_phase_stamps(long long* out20);
-
-/* Diagnostic: cycles per wait on an ALREADY COMPLETED mbarrier phase, one thread, dependent chain of `count` waits.
- * mode 0: mbarrier.try_wait with a suspend-time hint, 1: try_wait, 2: test_wait, 3: the kernels' bounded wait.
- * cycles_out2[0] = total SM cycles, [1] = number of waits that succeeded.  (Measured: 210 / 162 / 156 / 184 -- why
- * the pipelines are built to need few phase checks per unit of work.) */
-int sinc_mbar_wait_cost(int mode, int count, long long* cycles_out2, void* stream);
-
-/* Diagnostic: run `ksteps` tcgen05.mma (kind::tf32, M = 128) on caller-supplied shared-memory images and
- * raw matrix / instruction descriptors and return the 128 x N accumulator.  Not part of the replacement
- * surface (the reference has no counterpart); it exists so the operand layouts the tensor-core engine
- * relies on -- in-place Toeplitz descriptors over the waveform tile, TMEM-resident filter operand -- are
- * pinned by a hardware test (tests/test_gpu_tc_probe.py).  *status_out: 0 ok, 1 the MMA never completed. */
-int sinc_tc_probe(const void* imgA, int bytesA, const void* imgB, int bytesB, unsigned long long descA,
-                  unsigned long long descB, unsigned int idesc, int ksteps, int a_step, int b_step,
-                  int a_from_tmem, int a_cols, int N, float* D_out, int* status_out, void* stream);
-
-
-/* Diagnostic: cycles per tcgen05.mma (kind::f16, M = 128, N as given), `count` of them issued by one thread; the SM
- * cycle count of CTA 0 goes to cycles_out[0].  `a_from_tmem` is a bit field: bit 0 = A operand in TMEM (else shared
- * memory); bit 1 = non-zero operand data; bits 2..3 = instruction pattern (0: generic loop rotating through `nacc`
- * accumulators; 1: the forward kernel's sequence -- 17 K-steps x 3 products, B start += 32 bytes per K-step, `nacc` =
- * 1 one accumulator / 2 alternating / 3 runs of three; 2: the same with 128-byte aligned B starts; 3: pattern 1 with
- * a tcgen05.commit every `nacc` K-steps); bits 4..5 = what the CTA's other warps do meanwhile (0 nothing, 1
- * tcgen05.st, 2 LDS.128, 3 tcgen05.ld); bits 8..15 = number of CTAs (0 = one).  No counterpart in the reference;
- * tools/mma_rate*.py use it to establish what the tensor pipe costs and what it does not mind. */
-int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, long long* cycles_out, int* status_out, void* stream);
+/* A protocol failure inside a tcgen05 kernel (a pipeline barrier that never completes -- a bug, never a data-dependent
+ * condition) is LOUD: after 30 s of wall time on one barrier the kernel executes a trap, the launch fails with a sticky
+ * CUDA error and every later call returns it (> 0).  There is no way to obtain rc 0 with invalid results.
+ * Hardware probes and micro-benchmarks (operand-layout probe, MMA rate, mbarrier cost) are NOT part of this library:
+ * they live in libsinc_b200_diag.so (include/sinc_b200_diag.h), which only tests and tools load. */
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 // (overlapping core matrices, LBO = 16 B) and the TMEM A-operand layout were validated on B200.
 #include <type_traits>
 
+#include "sinc_b200_diag.h"
 #include "sinc_internal.h"
 #include "sinc_tc.cuh"
 
@@ -279,6 +280,40 @@ __global__ void __launch_bounds__(128, 1) tc_mma_rate_kernel(const RateArgs a) {
   if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
+// ---- register fragment of tcgen05.ld 16x256b.x8 (the grad-input epilogue's load shape) ------------------------------
+__global__ void __launch_bounds__(32, 1) ld16x256_probe_kernel(uint32_t* out) {
+  __shared__ uint32_t slot;
+  tc::tmem_alloc(&slot, 64);
+  tc::tmem_relinquish();
+  tc::fence_before_sync();
+  __syncwarp();
+  tc::fence_after_sync();
+  const uint32_t tm = slot;
+  const int lane = threadIdx.x;
+  for (int c0 = 0; c0 < 64; c0 += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 256u * lane + (uint32_t)(c0 + e);
+    tc::tmem_st8(tm + c0, v);   // 32x32b: thread = TMEM lane
+  }
+  tc::tmem_st_wait();
+  tc::fence_before_sync();
+  __syncwarp();
+  tc::fence_after_sync();
+  uint32_t lo[32], hi[32];
+  tc::tmem_ld16x256_x8(tm, lo);                  // lanes 0..15
+  tc::tmem_ld16x256_x8(tm + (16u << 16), hi);    // lanes 16..31
+  tc::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    out[lane * 64 + i] = lo[i];
+    out[lane * 64 + 32 + i] = hi[i];
+  }
+  tc::fence_before_sync();
+  __syncwarp();
+  tc::tmem_dealloc(tm, 64);
+}
+
 // ---- what a wait on an ALREADY COMPLETED mbarrier phase costs (cycles per wait, one thread, dependent chain) ----
 // mode 0: mbarrier.try_wait with the suspend-time hint (tc::mbar_try_wait), 1: try_wait without a hint,
 // 2: mbarrier.test_wait (non-blocking), 3: tc::mbar_wait (the kernels' bounded wait: test_wait, then try_wait polls)
@@ -315,6 +350,13 @@ __global__ void __launch_bounds__(32, 1) mbar_cost_kernel(int mode, int count, l
 }
 
 }  // namespace sinc
+
+extern "C" int sinc_tc_ld16x256_probe(uint32_t* out2048, void* stream) {
+  if (!out2048) return SINC_E_NULL;
+  sinc::ld16x256_probe_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(out2048);
+  sinc::count_launch();
+  return (int)cudaGetLastError();
+}
 
 extern "C" int sinc_mbar_wait_cost(int mode, int count, long long* cycles_out2, void* stream) {
   if (!cycles_out2 || count < 1 || mode < 0 || mode > 3) return SINC_E_SHAPE;

@@ -1,63 +1,30 @@
 // C ABI of libsinc_b200.so: argument validation, engine selection, launch accounting.
 // Declarations and the reference code each entry point replaces: include/sinc_b200.h.
-#include <atomic>
-#include <map>
-#include <mutex>
-#include <utility>
-
 #include "sinc_internal.h"
 
 namespace sinc {
 
-static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_engine{SINC_ENGINE_AUTO};
-// last engine mask: process-wide (backward runs on autograd's own thread, so thread-local would hide it)
-static std::atomic<int> t_last_mask{0};
-static std::atomic<int> g_reserved_sms{0};  // SMs the persistent backward kernels leave free (for a concurrent collective)
 // AUTO picks the tcgen05 kernel for a pass once that kernel is parity-green on hardware.
 constexpr bool kAutoPrefersTcForward = true;  // parity-green on B200 (tests/test_gpu_tc.py, r01c)
 constexpr bool kAutoPrefersTcBwdFilter = true;  // parity-green on B200 (r01h)
 constexpr bool kAutoPrefersTcBwdInput = true;   // parity-green on B200 (r01j)
 
-int reserved_sms() { return g_reserved_sms.load(std::memory_order_relaxed); }
-
-void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
-
-cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
-  static std::mutex mu;
-  static std::map<std::pair<const void*, int>, int> done;  // (kernel, device) -> bytes already granted
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  std::lock_guard<std::mutex> lock(mu);
-  auto key = std::make_pair(kernel, dev);
-  auto it = done.find(key);
-  if (it != done.end() && it->second >= bytes) return cudaSuccess;
-  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-  if (e == cudaSuccess) done[key] = bytes;
-  return e;
-}
-
-int get_device_info(DeviceInfo* out) {
-  static std::mutex mu;
-  static DeviceInfo cache[64];
-  static bool have[64] = {false};
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return (int)e;
-  if (dev < 0 || dev >= 64) return SINC_E_DEVICE;
-  std::lock_guard<std::mutex> lock(mu);
-  if (!have[dev]) {
-    DeviceInfo di;
-    if ((e = cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaDeviceGetAttribute(&di.cc_major, cudaDevAttrComputeCapabilityMajor, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaDeviceGetAttribute(&di.cc_minor, cudaDevAttrComputeCapabilityMinor, dev)) != cudaSuccess) return (int)e;
-    if ((e = cudaDeviceGetAttribute(&di.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev)) != cudaSuccess)
-      return (int)e;
-    cache[dev] = di;
-    have[dev] = true;
-  }
-  *out = cache[dev];
+// Per-call options with the defaults filled in (include/sinc_b200.h: sinc_options).  Nothing here outlives the call.
+struct Options {
+  int engine = SINC_ENGINE_AUTO;
+  int reserved_sms = 0;
+  int32_t* engines_used = nullptr;
+  long long* phase = nullptr;
+};
+static int read_options(const sinc_options* o, Options* out) {
+  if (!o) return 0;
+  if (o->engine < SINC_ENGINE_AUTO || o->engine > SINC_ENGINE_TC_TF32) return SINC_E_ENGINE;
+  if (o->reserved_sms < 0 || o->reserved_sms > 64) return SINC_E_SHAPE;
+  if (o->phase_stamps && reinterpret_cast<uintptr_t>(o->phase_stamps) % 8) return SINC_E_ALIGN;
+  out->engine = o->engine;
+  out->reserved_sms = o->reserved_sms;
+  out->engines_used = o->engines_used;
+  out->phase = o->phase_stamps;
   return 0;
 }
 
@@ -114,30 +81,7 @@ const char* sinc_strerror(int code) {
   return "sinc: unknown error";
 }
 
-uint64_t sinc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-
-int sinc_set_engine(int engine) {
-  if (engine < SINC_ENGINE_AUTO || engine > SINC_ENGINE_TC_TF32) return SINC_E_ENGINE;
-  g_engine.store(engine);
-  return 0;
-}
-int sinc_get_engine(void) { return g_engine.load(); }
-int sinc_set_reserved_sms(int n) {
-  if (n < 0 || n > 64) return SINC_E_SHAPE;
-  g_reserved_sms.store(n);
-  return 0;
-}
-int sinc_last_engine_mask(void) { return t_last_mask.load(); }
-
-int sinc_tc_phase_stamps(long long* out20) {
-  if (!out20) return SINC_E_NULL;
-  return read_tc_phase(out20);
-}
-
-int sinc_tc_status(int* status_host) {
-  if (!status_host) return SINC_E_NULL;
-  return read_tc_status(status_host);
-}
+uint64_t sinc_kernel_launch_count(void) { return launch_count(); }
 
 size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K) {
   (void)B;
@@ -157,9 +101,12 @@ int sinc_synthesize(const sinc_filterbank* fb, float* filters_out, void* stream)
 }
 
 int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, void* y, int32_t y_dtype,
-                 int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream) {
+                 int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream,
+                 const sinc_options* opts) {
   int r = check_bank(fb);
   if (r) return r;
+  Options o;
+  if ((r = read_options(opts, &o))) return r;
   if (!x || !y) return SINC_E_NULL;
   if (B < 1 || T < 1) return SINC_E_SHAPE;
   if (y_dtype != SINC_DTYPE_F32 && y_dtype != SINC_DTYPE_BF16) return SINC_E_DTYPE;
@@ -170,7 +117,7 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   DeviceInfo di;
   if ((r = check_device(&di))) return r;
   const Bank bank = to_bank(fb);
-  const int engine = g_engine.load();
+  const int engine = o.engine;
   const bool tc_ok = tc_fwd_supported(bank.C, bank.K, T, y, y_dtype, di);
   const bool tc16_ok = tc16_fwd_supported(bank.C, bank.K, T, y, y_dtype, di);
   if (engine == SINC_ENGINE_TC && !tc_ok && !tc16_ok) return SINC_E_ENGINE;
@@ -181,7 +128,7 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
   const bool use_tc = want_tc && tc_ok && !use_tc16;
   cudaError_t e;
   if (use_tc16) {
-    e = launch_fwd_tc16(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
+    e = launch_fwd_tc16(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream, nullptr, o.phase);
   } else if (use_tc) {
     e = launch_fwd_tc(bank, x, x_stride_b, y, B, T, di, (cudaStream_t)stream);
   } else {
@@ -189,16 +136,18 @@ int sinc_forward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, 
     e = launch_fwd_fma(bank, x, x_stride_b, y, y_dtype, B, T, di, (cudaStream_t)stream);
   }
   if (e != cudaSuccess) return (int)e;
-  t_last_mask.store((t_last_mask.load() & ~9) | ((use_tc || use_tc16) ? 1 : 0) | (use_tc16 ? 8 : 0));
+  if (o.engines_used) *o.engines_used = ((use_tc || use_tc16) ? 1 : 0) | (use_tc16 ? 8 : 0);
   return 0;
 }
 
 int64_t sinc_forward_gn_partials(int64_t T) { return tc16_fwd_tiles_per_row(T); }
 
 int sinc_forward_gn(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, float* y, int64_t B, int64_t T,
-                    float* gn_partial, void* stream) {
+                    float* gn_partial, void* stream, const sinc_options* opts) {
   int r = check_bank(fb);
   if (r) return r;
+  Options o;
+  if ((r = read_options(opts, &o))) return r;
   if (!x || !y || !gn_partial) return SINC_E_NULL;
   if (B < 1 || T < 1) return SINC_E_SHAPE;
   if (reinterpret_cast<uintptr_t>(x) % 4 || reinterpret_cast<uintptr_t>(y) % 4 || reinterpret_cast<uintptr_t>(gn_partial) % 8)
@@ -206,20 +155,23 @@ int sinc_forward_gn(const sinc_filterbank* fb, const float* x, int64_t x_stride_
   DeviceInfo di;
   if ((r = check_device(&di))) return r;
   const Bank bank = to_bank(fb);
-  const int engine = g_engine.load();
+  const int engine = o.engine;
   if (engine == SINC_ENGINE_FMA || engine == SINC_ENGINE_TC_TF32) return SINC_E_ENGINE;
   if (bank.C % 8 != 0 || !tc16_fwd_supported(bank.C, bank.K, T, y, SINC_DTYPE_F32, di)) return SINC_E_ENGINE;
-  cudaError_t e = launch_fwd_tc16(bank, x, x_stride_b, y, SINC_DTYPE_F32, B, T, di, (cudaStream_t)stream, gn_partial);
+  cudaError_t e = launch_fwd_tc16(bank, x, x_stride_b, y, SINC_DTYPE_F32, B, T, di, (cudaStream_t)stream, gn_partial, o.phase);
   if (e != cudaSuccess) return (int)e;
-  t_last_mask.store((t_last_mask.load() & ~9) | 9);
+  if (o.engines_used) *o.engines_used = 9;
   return 0;
 }
 
 int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b, const void* grad_y,
                   int32_t gy_dtype, float* grad_x, float* grad_low, float* grad_band, float* grad_filters,
-                  int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream) {
+                  int64_t B, int64_t T, void* workspace, size_t workspace_bytes, void* stream,
+                  const sinc_options* opts) {
   int r = check_bank(fb);
   if (r) return r;
+  Options o;
+  if ((r = read_options(opts, &o))) return r;
   if (!grad_y) return SINC_E_NULL;
   if ((grad_low == nullptr) != (grad_band == nullptr)) return SINC_E_NULL;
   const bool want_params = grad_low != nullptr || grad_filters != nullptr;
@@ -234,7 +186,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
   int mask = 0;
-  const int engine = g_engine.load();
+  const int engine = o.engine;
   // The filter table (sinc_synth.cuh): written by the 16-bit grad-filter kernel, read -- after validation -- by the
   // 16-bit grad-input kernel.  Parameter gradients therefore go first when both are wanted; a grad-input-only call
   // finds the table of the preceding parameter-gradient call on the same workspace (data parallel: the all-reduce
@@ -257,7 +209,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
     if (use_tc16)
-      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table);
+      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table, o.phase);
     else if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else
@@ -277,7 +229,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
     if (use_tc16)
-      e = launch_bwd_input_tc16(bank, grad_y, gy_dtype, grad_x, B, T, di, st, filter_table);
+      e = launch_bwd_input_tc16(bank, grad_y, gy_dtype, grad_x, B, T, di, st, filter_table, o.reserved_sms, o.phase);
     else if (use_tc)
       e = launch_bwd_input_tc(bank, grad_y, grad_x, B, T, di, st);
     else
@@ -286,7 +238,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     mask |= (use_tc || use_tc16) ? 2 : 0;
     mask |= use_tc16 ? 16 : 0;
   }
-  t_last_mask.store((t_last_mask.load() & 9) | mask);
+  if (o.engines_used) *o.engines_used = mask;
   return 0;
 }
 

@@ -10,7 +10,9 @@
 // partial sums (bitwise reproducible).
 //
 // Layout: y, z, dz, dy are (B,C,T) contiguous; a group's C/G channels are contiguous, so a (b,g) slab is one
-// contiguous run of (C/G)*T elements.  Requirements: T % 4 == 0, 16-byte aligned pointers.
+// contiguous run of (C/G)*T elements.  16-byte accesses when T % 4 == 0 and the tensors are 16-byte aligned (template
+// flag V); any other length or alignment takes the same kernels with 4-byte accesses -- the reference's
+// gelu(GroupNorm(.)) accepts any length, so the drop-in does too (at roughly a quarter of the bandwidth).
 #include <cuda_bf16.h>
 
 #include "sinc_internal.h"
@@ -52,6 +54,7 @@ __device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch
 
 // ---- K1: per-chunk partial sums of y and y^2 ------------------------------------------------------------------
 // grid = (B*C, chunks_per_row); partial[(b*C + c) * chunks_per_row + chunk] = (sum, sum of squares)
+template <bool V>
 __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __restrict__ y, int64_t T, int chunks_per_row,
                                                               float2* __restrict__ partial) {
   __shared__ double scratch[64];
@@ -59,13 +62,23 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const float* __res
   const int chunk = blockIdx.y;
   const int64_t t0 = (int64_t)chunk * GN_CHUNK;
   const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
-  const float4* p = reinterpret_cast<const float4*>(y + row * T + t0);
   float s = 0.f, q = 0.f;
+  if constexpr (V) {
+    const float4* p = reinterpret_cast<const float4*>(y + row * T + t0);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
-    const float4 v = __ldg(p + i);
-    s += (v.x + v.y) + (v.z + v.w);
-    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+      const float4 v = __ldg(p + i);
+      s += (v.x + v.y) + (v.z + v.w);
+      q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
+  } else {
+    const float* p = y + row * T + t0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += GN_THREADS) {
+      const float v = __ldg(p + i);
+      s += v;
+      q = fmaf(v, v, q);
+    }
   }
   double ds = s, dq = q;
   block_sum2(ds, dq, scratch);
@@ -91,6 +104,7 @@ __device__ __forceinline__ void group_moments(const float2* __restrict__ partial
 
 // ---- K2: z = gelu(gamma_c * (y - mean) * rstd + beta_c) -----------------------------------------------------
 // grid = (B*C, chunks_per_row); also writes stats[(b*G + g)] = (mean, rstd) (first chunk of the group's first channel)
+template <bool V>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_gelu_kernel(const float* __restrict__ y, const float2* __restrict__ partial, int np, int rows_per_group,
                      const float* __restrict__ gamma,
@@ -111,21 +125,29 @@ gn_apply_gelu_kernel(const float* __restrict__ y, const float2* __restrict__ par
   const float a = __ldg(gamma + c) * rstd, sh = __ldg(beta + c) - mean * a;  // u = a*y + sh
   const int64_t t0 = (int64_t)chunk * GN_CHUNK;
   const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
-  const float4* p = reinterpret_cast<const float4*>(y + row * T + t0);
-  float4* o = reinterpret_cast<float4*>(z + row * T + t0);
+  if constexpr (V) {
+    const float4* p = reinterpret_cast<const float4*>(y + row * T + t0);
+    float4* o = reinterpret_cast<float4*>(z + row * T + t0);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
-    const float4 v = __ldg(p + i);
-    float4 r;
-    r.x = gelu_f(fmaf(a, v.x, sh));
-    r.y = gelu_f(fmaf(a, v.y, sh));
-    r.z = gelu_f(fmaf(a, v.z, sh));
-    r.w = gelu_f(fmaf(a, v.w, sh));
-    o[i] = r;
+    for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+      const float4 v = __ldg(p + i);
+      float4 r;
+      r.x = gelu_f(fmaf(a, v.x, sh));
+      r.y = gelu_f(fmaf(a, v.y, sh));
+      r.z = gelu_f(fmaf(a, v.z, sh));
+      r.w = gelu_f(fmaf(a, v.w, sh));
+      o[i] = r;
+    }
+  } else {
+    const float* p = y + row * T + t0;
+    float* o = z + row * T + t0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += GN_THREADS) o[i] = gelu_f(fmaf(a, __ldg(p + i), sh));
   }
 }
 
 // ---- K3: backward partial sums per channel chunk: (sum du*yhat, sum du), du = dz * gelu'(u) ------------------
+template <bool V>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_stats_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float2* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, float2* __restrict__ partial, int64_t T,
@@ -140,20 +162,29 @@ gn_bwd_stats_kernel(const float* __restrict__ dz, const float* __restrict__ y, c
   const int chunk = blockIdx.y;
   const int64_t t0 = (int64_t)chunk * GN_CHUNK;
   const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
-  const float4* pz = reinterpret_cast<const float4*>(dz + row * T + t0);
-  const float4* py = reinterpret_cast<const float4*>(y + row * T + t0);
   float s1 = 0.f, s0 = 0.f;
+  auto one = [&](float d, float v) {
+    const float yh = (v - mean) * rstd;
+    const float du = d * gelu_grad_f(fmaf(ga, yh, be));
+    s1 = fmaf(du, yh, s1);
+    s0 += du;
+  };
+  if constexpr (V) {
+    const float4* pz = reinterpret_cast<const float4*>(dz + row * T + t0);
+    const float4* py = reinterpret_cast<const float4*>(y + row * T + t0);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
-    const float4 d = __ldg(pz + i), v = __ldg(py + i);
-    const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float yh = (vv[e] - mean) * rstd;
-      const float du = dd[e] * gelu_grad_f(fmaf(ga, yh, be));
-      s1 = fmaf(du, yh, s1);
-      s0 += du;
+    for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+      const float4 d = __ldg(pz + i), v = __ldg(py + i);
+      one(d.x, v.x);
+      one(d.y, v.y);
+      one(d.z, v.z);
+      one(d.w, v.w);
     }
+  } else {
+    const float* pz = dz + row * T + t0;
+    const float* py = y + row * T + t0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += GN_THREADS) one(__ldg(pz + i), __ldg(py + i));
   }
   double d1 = s1, d0 = s0;
   block_sum2(d1, d0, scratch);
@@ -161,6 +192,7 @@ gn_bwd_stats_kernel(const float* __restrict__ dz, const float* __restrict__ y, c
 }
 
 // ---- K4: dy = rstd * (dyhat - m0 - yhat * m1),  dyhat = gamma_c * du, m = group means of dyhat, dyhat*yhat ----
+template <bool V>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, const float2* __restrict__ stats,
                     const float2* __restrict__ partial, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -187,21 +219,26 @@ gn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y, c
   const int chunk = blockIdx.y;
   const int64_t t0 = (int64_t)chunk * GN_CHUNK;
   const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
-  const float4* pz = reinterpret_cast<const float4*>(dz + row * T + t0);
-  const float4* py = reinterpret_cast<const float4*>(y + row * T + t0);
-  float4* po = reinterpret_cast<float4*>(dy + row * T + t0);
+  auto one = [&](float d, float v) -> float {
+    const float yh = (v - mean) * rstd;
+    const float dyh = ga * d * gelu_grad_f(fmaf(ga, yh, be));
+    return rstd * (dyh - f0 - yh * f1);
+  };
+  if constexpr (V) {
+    const float4* pz = reinterpret_cast<const float4*>(dz + row * T + t0);
+    const float4* py = reinterpret_cast<const float4*>(y + row * T + t0);
+    float4* po = reinterpret_cast<float4*>(dy + row * T + t0);
 #pragma unroll 4
-  for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
-    const float4 d = __ldg(pz + i), v = __ldg(py + i);
-    const float dd[4] = {d.x, d.y, d.z, d.w}, vv[4] = {v.x, v.y, v.z, v.w};
-    float r[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float yh = (vv[e] - mean) * rstd;
-      const float dyh = ga * dd[e] * gelu_grad_f(fmaf(ga, yh, be));
-      r[e] = rstd * (dyh - f0 - yh * f1);
+    for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
+      const float4 d = __ldg(pz + i), v = __ldg(py + i);
+      po[i] = make_float4(one(d.x, v.x), one(d.y, v.y), one(d.z, v.z), one(d.w, v.w));
     }
-    po[i] = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+    const float* pz = dz + row * T + t0;
+    const float* py = y + row * T + t0;
+    float* po = dy + row * T + t0;
+#pragma unroll 4
+    for (int i = threadIdx.x; i < n; i += GN_THREADS) po[i] = one(__ldg(pz + i), __ldg(py + i));
   }
 }
 
@@ -228,10 +265,14 @@ gn_param_grad_kernel(const float2* __restrict__ partial, int64_t B, int C, int c
 
 static int gn_check(int64_t B, int64_t T, int C, int G, const void* a, const void* b2) {
   if (B < 1 || T < 1 || C < 1 || G < 1 || C % G) return SINC_E_SHAPE;
-  if (T % 4) return SINC_E_UNSUPPORTED;
-  if (reinterpret_cast<uintptr_t>(a) % 16 || reinterpret_cast<uintptr_t>(b2) % 16) return SINC_E_ALIGN;
+  if (reinterpret_cast<uintptr_t>(a) % 4 || reinterpret_cast<uintptr_t>(b2) % 4) return SINC_E_ALIGN;
   if (B * C > 2147483647LL) return SINC_E_SHAPE;
   return 0;
+}
+// 16-byte accesses need every row start 16-byte aligned
+static bool gn_vec(int64_t T, const void* a, const void* b2, const void* c3 = nullptr) {
+  return T % 4 == 0 && reinterpret_cast<uintptr_t>(a) % 16 == 0 && reinterpret_cast<uintptr_t>(b2) % 16 == 0 &&
+         reinterpret_cast<uintptr_t>(c3) % 16 == 0;
 }
 
 }  // namespace sinc
@@ -247,8 +288,8 @@ int sinc_gn_stats(const float* y, int64_t B, int64_t T, int32_t C, float* partia
   int r = gn_check(B, T, C, 1, y, y);
   if (r) return r;
   const int cpr = sinc_gn_chunks(T);
-  gn_stats_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, (cudaStream_t)stream>>>(y, T, cpr,
-                                                                                         reinterpret_cast<float2*>(partial));
+  auto kern = gn_vec(T, y, y) ? gn_stats_kernel<true> : gn_stats_kernel<false>;
+  kern<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, (cudaStream_t)stream>>>(y, T, cpr, reinterpret_cast<float2*>(partial));
   count_launch();
   return (int)cudaGetLastError();
 }
@@ -261,7 +302,8 @@ int sinc_gn_gelu_forward(const float* y, const float* partial, int32_t np, int32
   if (r) return r;
   if (np < 1 || (rows_per_group != 1 && rows_per_group != C / G)) return SINC_E_SHAPE;
   const int cpr = sinc_gn_chunks(T);
-  gn_apply_gelu_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, (cudaStream_t)stream>>>(
+  auto kern = gn_vec(T, y, z) ? gn_apply_gelu_kernel<true> : gn_apply_gelu_kernel<false>;
+  kern<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, (cudaStream_t)stream>>>(
       y, reinterpret_cast<const float2*>(partial), np, rows_per_group, gamma, beta, z, reinterpret_cast<float2*>(stats), T, C, G,
       cpr, eps);
   count_launch();
@@ -275,13 +317,16 @@ int sinc_gn_gelu_backward(const float* dz, const float* y, const float* stats, c
   if ((dgamma == nullptr) != (dbeta == nullptr)) return SINC_E_NULL;
   int r = gn_check(B, T, C, G, dz, y);
   if (r) return r;
-  if (reinterpret_cast<uintptr_t>(dy) % 16) return SINC_E_ALIGN;
+  if (reinterpret_cast<uintptr_t>(dy) % 4) return SINC_E_ALIGN;
   const int cpr = sinc_gn_chunks(T);
   cudaStream_t st = (cudaStream_t)stream;
-  gn_bwd_stats_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, st>>>(dz, y, reinterpret_cast<const float2*>(stats), gamma,
+  const bool vec = gn_vec(T, dz, y, dy);
+  auto kstats = vec ? gn_bwd_stats_kernel<true> : gn_bwd_stats_kernel<false>;
+  auto kapply = vec ? gn_bwd_apply_kernel<true> : gn_bwd_apply_kernel<false>;
+  kstats<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, st>>>(dz, y, reinterpret_cast<const float2*>(stats), gamma,
                                                                              beta, reinterpret_cast<float2*>(partial), T, C, G, cpr);
   count_launch();
-  gn_bwd_apply_kernel<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, st>>>(dz, y, reinterpret_cast<const float2*>(stats),
+  kapply<<<dim3((unsigned)(B * C), cpr), GN_THREADS, 0, st>>>(dz, y, reinterpret_cast<const float2*>(stats),
                                                                              reinterpret_cast<const float2*>(partial), gamma, beta,
                                                                              dy, T, C, G, cpr);
   count_launch();

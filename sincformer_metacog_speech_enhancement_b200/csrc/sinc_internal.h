@@ -44,7 +44,7 @@ struct DeviceInfo {
 int get_device_info(DeviceInfo* out);
 
 void count_launch(int n = 1);
-int reserved_sms();  // sinc_set_reserved_sms(): SMs the persistent grad-input kernel leaves free
+uint64_t launch_count();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch
 cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
 
@@ -87,10 +87,6 @@ cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slot
 bool tc_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di);
 cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int64_t B, int64_t T,
                           const DeviceInfo& di, cudaStream_t st);
-int read_tc_status(int* out);
-long long* tc_phase_device_ptr();  // device address of the phase time stamps (see sinc_tc_fwd.cu)
-int read_tc_phase(long long* out20);
-int* tc_status_device_ptr();  // device address of the shared 'barrier wait timed out' flag
 bool tc_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 size_t tc_bwd_filter_partial_bytes(int C);
 cudaError_t launch_bwd_filter_tc(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, float* ws_partials,
@@ -104,15 +100,16 @@ cudaError_t launch_bwd_input_tc(const Bank& bank, const void* gy, float* gx, int
 // 16-bit split variants (bf16 hi/mid, three kind::f16 MMAs): sinc_tc16_*.cu
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
-                                  const DeviceInfo& di, cudaStream_t st, const uint8_t* filter_table);
+                                  const DeviceInfo& di, cudaStream_t st, const uint8_t* filter_table, int reserved_sms,
+                                  long long* phase);
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di);
 cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b, void* y, int y_dtype, int64_t B,
-                            int64_t T, const DeviceInfo& di, cudaStream_t st, float* gn_partial = nullptr);
+                            int64_t T, const DeviceInfo& di, cudaStream_t st, float* gn_partial, long long* phase);
 int64_t tc16_fwd_tiles_per_row(int64_t T);
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 size_t tc16_bwd_filter_partial_bytes(int C);
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st, uint8_t* filter_table);
+                                   cudaStream_t st, uint8_t* filter_table, long long* phase);
 
 }  // namespace sinc

@@ -129,6 +129,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+// 16 TMEM lanes x 64 columns as the 16x256b fragment: thread t of the warp receives, for j = 0..7, u = 0..1, e = 0..1,
+//     v[4*j + 2*u + e] = TMEM[lane0 + (t / 4) + 8*u][col0 + 8*j + 2*(t % 4) + e]
+// (the mma.sync-style accumulator fragment; pinned on hardware by the diagnostics library's sinc_tc_ld16x256_probe).
+// A thread therefore holds two ROWS eight lanes apart for the same columns -- what lets the grad-input epilogue add
+// rows of the accumulator that belong to the same output sample without any cross-thread traffic.
+__device__ __forceinline__ void tmem_ld16x256_x8(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
@@ -154,9 +169,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must end in a wrong answer (caught by the parity tests), never in a hung GPU.
-// The bound is one second of wall time (%globaltimer); callers short-circuit (`ok = ok && mbar_wait(..)`) so a
-// role that has timed out once stops waiting and the kernel drains within a couple of seconds.
+// Bounded wait: a protocol bug must never end in a hung GPU -- and never in a silently wrong answer either.  After
+// kWaitLimitNs of wall time (%globaltimer) on ONE barrier the thread executes a trap: the launch fails with a sticky
+// CUDA error that the next API call of the host reports (include/sinc_b200.h).  The bound is long enough for
+// compute-sanitizer, ncu replay, cuda-gdb single-stepping of another warp and time-sliced contexts; the polls back
+// off with the suspend-time hint of mbarrier.try_wait, so a long wait costs no issue slots.
+// The diagnostics library (-DSINC_DIAG_SOFT_TIMEOUT) keeps the non-trapping variant: its probes report a timeout
+// through their own status word.  Callers keep the `ok = ok && mbar_wait(..)` form; in the product `ok` stays true.
+constexpr unsigned long long kWaitLimitNs =
+#ifdef SINC_DIAG_SOFT_TIMEOUT
+    1000000000ull;
+#else
+    30000000000ull;
+#endif
 __device__ __forceinline__ uint64_t global_timer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -186,7 +211,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 #pragma unroll 1
     for (int spin = 0; spin < 256; ++spin)
       if (mbar_try_wait(bar, parity)) return true;
-    if (global_timer_ns() - t0 > 1000000000ull) return false;
+    if (global_timer_ns() - t0 > kWaitLimitNs) {
+#ifdef SINC_DIAG_SOFT_TIMEOUT
+      return false;
+#else
+      __trap();
+#endif
+    }
   }
 }
 

@@ -28,13 +28,6 @@
 
 namespace sinc {
 
-// set to 1 by any tcgen05 kernel whose barrier wait timed out (a protocol bug): read by sinc_tc_status()
-__device__ int g_tc_status = 0;
-// diagnostic time stamps of the last launch of each 16-bit tcgen05 kernel (CTA 0): {clock64, globaltimer ns} at
-// entry, after the prologue, at exit -- [0,6) forward, [6,12) grad-input, [12,18) grad-filter; [18] = 1 if that
-// grad-input launch took its filters from the workspace table (sinc_synth.cuh)
-__device__ long long g_tc_phase[20];
-
 constexpr int TF_THREADS = 224;  // warps 0-3 epilogue, 4 and 6 MMA issuers (even / odd tiles), 5 waveform producer
 constexpr int TF_FB = 32;                 // filters per CTA
 constexpr int TF_NJ = 128;                // MMA N: output groups of 4 samples per tile
@@ -255,7 +248,7 @@ __global__ void __launch_bounds__(TF_THREADS, 1) fwd_tc_kernel(const FwdTcArgs a
     }
     if (lane < 8) tc::bulk_wait<0>();
   }
-  if (!ok && lane == 0) g_tc_status = 1;
+  (void)ok;  // mbar_wait traps on a timeout (sinc_tc.cuh): no silent failure path
   tc::fence_before_sync();
   __syncthreads();
   if (warp == 4) tc::tmem_dealloc(tmem, 512);
@@ -290,29 +283,6 @@ cudaError_t launch_fwd_tc(const Bank& bank, const float* x, int64_t x_stride_b, 
   fwd_tc_kernel<<<grid, TF_THREADS, smem, st>>>(a);
   count_launch();
   return cudaGetLastError();
-}
-
-int* tc_status_device_ptr() {
-  void* p = nullptr;
-  if (cudaGetSymbolAddress(&p, g_tc_status) != cudaSuccess) return nullptr;
-  return reinterpret_cast<int*>(p);
-}
-
-long long* tc_phase_device_ptr() {
-  void* p = nullptr;
-  if (cudaGetSymbolAddress(&p, g_tc_phase) != cudaSuccess) return nullptr;
-  return reinterpret_cast<long long*>(p);
-}
-int read_tc_phase(long long* out20) {
-  return (int)cudaMemcpyFromSymbol(out20, g_tc_phase, 20 * sizeof(long long));
-}
-
-int read_tc_status(int* out) {
-  int v = 0;
-  cudaError_t e = cudaMemcpyFromSymbol(&v, g_tc_status, sizeof(int));
-  if (e != cudaSuccess) return (int)e;
-  *out = v;
-  return 0;
 }
 
 }  // namespace sinc

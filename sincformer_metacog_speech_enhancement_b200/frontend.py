@@ -17,7 +17,8 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .sinc import SincConv1d, SincConvFunction, _bank, _ptr, _small
+from . import sinc as _sinc
+from .sinc import SincConv1d, SincConvFunction, _bank, _check_input, _options, _ptr, _small
 
 
 def _stream(dev):
@@ -36,8 +37,8 @@ class _GroupNormGELU(torch.autograd.Function):
             raise RuntimeError("FusedGroupNormGELU (B200): expects a float32 CUDA tensor (batch, channels, samples)")
         y = y.contiguous()
         B, C, T = y.shape
-        if C % G or T % 4:
-            raise RuntimeError(f"FusedGroupNormGELU: need channels % groups == 0 and samples % 4 == 0, got C={C} G={G} T={T}")
+        if C % G:
+            raise RuntimeError(f"FusedGroupNormGELU: need channels % groups == 0, got C={C} G={G}")
         dev = y.device
         w = _small(weight, "weight", dev)
         b = _small(bias, "bias", dev)
@@ -107,8 +108,9 @@ class _SincConvWithStats(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz):
+    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, engine=None, debug=None):
         lib = _lib.load()
+        _check_input(x)           # the same device / shape / dtype / empty-input rules as SincConv1d.forward
         dev = x.device
         low, band = _small(low_hz_, "low_hz_", dev), _small(band_hz_, "band_hz_", dev)
         win, nn_ = _small(window, "window", dev), _small(n_, "n_", dev)
@@ -120,14 +122,17 @@ class _SincConvWithStats(torch.autograd.Function):
         y = torch.empty((B, C, T), dtype=torch.float32, device=dev)
         partial = torch.empty((B, C // 8, lib.sinc_forward_gn_partials(T), 2), dtype=torch.float32, device=dev)
         fb = _bank(low, band, win, nn_, sample_rate, min_low_hz, min_band_hz)
+        opts, _ = _options(engine)
         with torch.cuda.device(dev):
             rc = lib.sinc_forward_gn(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(y), B, T,
-                                     _ptr(partial), _stream(dev))
+                                     _ptr(partial), _stream(dev), ctypes.byref(opts))
         _lib.check(rc, "sinc_forward_gn")
         ctx.save_for_backward(xd, low, band, win, nn_)
         ctx.attrs = (float(sample_rate), float(min_low_hz), float(min_band_hz))
-        ctx.expose_grad_filters = False
         ctx.sync = None
+        ctx.engine = engine
+        ctx.debug = debug
+        ctx.in_dtypes = (x.dtype, low_hz_.dtype, band_hz_.dtype)
         ctx.mark_non_differentiable(partial)
         return y, partial
 
@@ -135,7 +140,7 @@ class _SincConvWithStats(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_y, _grad_partial):
         out = SincConvFunction.backward(ctx, grad_y)
-        return out[:8]
+        return out[:10]
 
 
 class SincFrontEnd(nn.Module):
@@ -160,10 +165,11 @@ class SincFrontEnd(nn.Module):
             waveform = waveform.unsqueeze(1)           # (batch, samples) as in PerceptionAgent.forward :228-229
         sc, gn = self.sinc_conv, self.sinc_norm
         C, T = sc.out_channels, waveform.shape[-1]
+        engine = sc.engine or _sinc._default_engine
         fused = (gn.num_channels // gn.num_groups == 8 and C % 8 == 0 and T % 4 == 0 and sc.kernel_size <= 265
-                 and waveform.dtype == torch.float32 and _lib.load().sinc_get_engine() in (_lib.ENGINE_AUTO, _lib.ENGINE_TC))
+                 and waveform.dtype == torch.float32 and sc.low_hz_.dtype == torch.float32 and engine in ("auto", "tc"))
         if fused:
             y, partial = _SincConvWithStats.apply(waveform, sc.low_hz_, sc.band_hz_, sc.window, sc.n_, sc.sample_rate,
-                                                  sc.min_low_hz, sc.min_band_hz)
+                                                  sc.min_low_hz, sc.min_band_hz, sc.engine, sc._debug)
             return gn(y, partial)
         return gn(sc(waveform))

@@ -22,6 +22,11 @@ import torch.nn as nn
 
 from . import _lib
 
+import contextlib
+import os
+
+_NVTX = os.environ.get("SINC_NVTX", "1") != "0"   # NVTX ranges around the C-ABI calls; ~1 us each
+_null_ctx = contextlib.nullcontext()
 _FALLBACK_SAMPLE_RATE = 8000  # reference config.py:17
 _SYNC_RESERVED_SMS = 4        # SMs left to NCCL while the grad-input kernel runs (enable_grad_sync)
 
@@ -72,13 +77,33 @@ def _bank(low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz):
 
 
 def _small(t: torch.Tensor, name: str, device) -> torch.Tensor:
+    """One of the four small state tensors as a contiguous fp32 device tensor.  A module cast with .double() /
+    .bfloat16() / .half() keeps working like the reference's does (SURVEY 8a edge list): its state is read at its
+    stored values and the arithmetic stays fp32 (documented deviation: the reference would compute in that dtype)."""
     if t.device != device:
         raise RuntimeError(f"SincConv1d: {name} is on {t.device}, input is on {device}")
-    if t.dtype != torch.float32:
-        raise RuntimeError(f"SincConv1d: {name} must be float32 (got {t.dtype}); the B200 path computes "
-                           "in fp32 and does not follow .double()/.half() casts of the module")
+    if not t.is_floating_point():
+        raise RuntimeError(f"SincConv1d: {name} must be a floating-point tensor (got {t.dtype})")
     t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
     return t if t.is_contiguous() else t.contiguous()
+
+
+_default_engine = "auto"   # package default for modules that do not set their own (set_engine() in __init__.py)
+
+
+def _options(engine=None, reserved_sms=0, want_mask=False, phase_stamps=None):
+    """sinc_options for one call (include/sinc_b200.h).  Returns (options, mask holder or None)."""
+    o = _lib.Options()
+    o.engine = _lib.ENGINE_CODES[engine or _default_engine]
+    o.reserved_sms = reserved_sms
+    holder = ctypes.c_int32(0) if want_mask else None
+    if holder is not None:
+        o.engines_used = ctypes.pointer(holder)
+    if phase_stamps is not None:
+        o.phase_stamps = phase_stamps.data_ptr()
+    return o, holder
 
 
 class _on_device:
@@ -96,15 +121,25 @@ class _on_device:
             self.ctx.__exit__(*exc)
 
 
-def _forward_impl(x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype):
-    """Argument checks + the sinc_forward call; returns (y, tensors to save for backward)."""
-    lib = _lib.load()
+def _check_input(x, param_dtype=torch.float32):
+    """The reference's shape / device / dtype rules for the waveform (agents/perception.py:117: F.conv1d raises when
+    the input dtype differs from the weight dtype)."""
     if not x.is_cuda:
         raise RuntimeError("SincConv1d (B200): input must be a CUDA tensor -- this implementation has no CPU path")
     if x.dim() != 3 or x.shape[1] != 1:
         raise RuntimeError(f"SincConv1d expects (batch, 1, samples); got {tuple(x.shape)}")
-    if x.dtype != torch.float32:
-        raise RuntimeError(f"SincConv1d: input must be float32 (got {x.dtype})")
+    if x.dtype != param_dtype:
+        raise RuntimeError(f"SincConv1d: input type ({x.dtype}) and parameter type ({param_dtype}) should be the same")
+    if x.shape[0] == 0 or x.shape[2] == 0:
+        raise RuntimeError("SincConv1d: empty input")
+
+
+def _forward_impl(x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype, engine=None,
+                  record=None):
+    """Argument checks + the sinc_forward call; returns (y, tensors to save for backward).  `x` is fp32 here (a cast
+    module converts before calling)."""
+    lib = _lib.load()
+    _check_input(x)
     dev = x.device
     low = _small(low_hz_, "low_hz_", dev)
     band = _small(band_hz_, "band_hz_", dev)
@@ -117,15 +152,17 @@ def _forward_impl(x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min
     if xd.stride(2) != 1 and xd.shape[2] > 1:
         xd = xd.contiguous()
     B, _, T = xd.shape
-    if B == 0 or T == 0:
-        raise RuntimeError("SincConv1d: empty input")
     y = torch.empty((B, C, T), dtype=out_dtype, device=dev)
     fb = _bank(low, band, win, nn_, sample_rate, min_low_hz, min_band_hz)
+    opts, mask = _options(engine, want_mask=record is not None, phase_stamps=None if record is None else record.get("phase_stamps"))
     with _on_device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = lib.sinc_forward(ctypes.byref(fb), _ptr(xd), xd.stride(0) if B > 1 else T, _ptr(y),
-                              _dtype_code(out_dtype), B, T, None, 0, ctypes.c_void_p(stream))  # no scratch needed
+                              _dtype_code(out_dtype), B, T, None, 0, ctypes.c_void_p(stream),  # no scratch needed
+                              ctypes.byref(opts))
     _lib.check(rc, "sinc_forward")
+    if record is not None:
+        record["fwd"] = _lib.decode_engines(mask.value)["fwd"]
     return y, (xd, low, band, win, nn_)
 
 
@@ -136,17 +173,26 @@ def _workspace(B, T, C, K, device):
 
 class SincConvFunction(torch.autograd.Function):
     """y = conv1d(x, synth(low_hz_, band_hz_; window, n_), stride=1, padding=K//2) with a hand-written
-    backward: grad-input plus the parameter gradients through the synthesis chain rule (fp64)."""
+    backward: grad-input plus the parameter gradients through the synthesis chain rule (fp64).
+
+    `sync` = (process group, average) or None: data-parallel all-reduce of the parameter gradients inside backward.
+    `debug` = None or a dict owned by the calling module instance: receives 'grad_filters' (the intermediate (C,K)
+    dL/dw, when the dict has the key 'want_grad_filters') and the engines that ran -- an explicit, per-instance debug
+    channel (no class-level state)."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype, sync=None):
-        y, (xd, low, band, win, nn_) = _forward_impl(x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz,
-                                                     min_band_hz, out_dtype)
+    def forward(ctx, x, low_hz_, band_hz_, window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype, sync=None,
+                engine=None, debug=None):
+        y, (xd, low, band, win, nn_) = _forward_impl(x.float() if x.dtype != torch.float32 else x, low_hz_, band_hz_,
+                                                     window, n_, sample_rate, min_low_hz, min_band_hz, out_dtype,
+                                                     engine, debug)
         ctx.save_for_backward(xd, low, band, win, nn_)
         ctx.attrs = (float(sample_rate), float(min_low_hz), float(min_band_hz))
-        ctx.expose_grad_filters = getattr(SincConvFunction, "_expose_grad_filters", False)
         ctx.sync = sync
+        ctx.engine = engine
+        ctx.debug = debug
+        ctx.in_dtypes = (x.dtype, low_hz_.dtype, band_hz_.dtype)
         return y
 
     @staticmethod
@@ -158,6 +204,7 @@ class SincConvFunction(torch.autograd.Function):
         sr, min_low, min_band = ctx.attrs
         need_x = ctx.needs_input_grad[0]
         need_p = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        debug = ctx.debug
         dev = xd.device
         B, _, T = xd.shape
         C, K = low.numel(), win.numel()
@@ -168,46 +215,58 @@ class SincConvFunction(torch.autograd.Function):
         gx = torch.empty((B, 1, T), dtype=torch.float32, device=dev) if need_x else None
         gp = torch.empty((2, C, 1), dtype=torch.float32, device=dev) if need_p else None
         gfilt = None
-        if need_p and ctx.expose_grad_filters:
+        if need_p and debug is not None and debug.get("want_grad_filters"):
             gfilt = torch.empty((C, K), dtype=torch.float32, device=dev)
         if need_x or need_p:
             fb = _bank(low, band, win, nn_, sr, min_low, min_band)
             ws, ws_bytes = _workspace(B, T, C, K, dev)
             xs0 = xd.stride(0) if B > 1 else T
+            used = 0
 
-            def launch(want_x, want_p):
+            def launch(want_x, want_p, reserved_sms=0):
+                opts, mask = _options(ctx.engine, reserved_sms, want_mask=debug is not None,
+                                      phase_stamps=None if debug is None else debug.get("phase_stamps"))
                 with _on_device(dev):
                     stream = torch.cuda.current_stream(dev).cuda_stream
-                    rc = lib.sinc_backward(ctypes.byref(fb), _ptr(xd), xs0, _ptr(g), _dtype_code(g.dtype),
-                                           _ptr(gx if want_x else None), _ptr(gp[0] if want_p else None),
-                                           _ptr(gp[1] if want_p else None), _ptr(gfilt if want_p else None), B, T,
-                                           _ptr(ws), ws_bytes, ctypes.c_void_p(stream))
+                    with torch.cuda.nvtx.range("sinc_backward:" + ("grad_input+" if want_x else "") +
+                                               ("grad_filter" if want_p else "")) if _NVTX else _null_ctx:
+                        rc = lib.sinc_backward(ctypes.byref(fb), _ptr(xd), xs0, _ptr(g), _dtype_code(g.dtype),
+                                               _ptr(gx if want_x else None), _ptr(gp[0] if want_p else None),
+                                               _ptr(gp[1] if want_p else None), _ptr(gfilt if want_p else None), B, T,
+                                               _ptr(ws), ws_bytes, ctypes.c_void_p(stream), ctypes.byref(opts))
                 _lib.check(rc, "sinc_backward")
+                return mask.value if mask is not None else 0
 
             sync = ctx.sync
             if need_p and sync is not None and torch.distributed.is_available() and torch.distributed.is_initialized():
                 # data-parallel: parameter gradients first, their 2*C-float all-reduce (the only exchange of the
                 # path) is then in flight on NCCL's stream while grad-input runs
                 group, average = sync
-                launch(False, True)
+                used |= launch(False, True)
                 work = torch.distributed.all_reduce(gp, op=torch.distributed.ReduceOp.SUM, group=group, async_op=True)
                 if need_x:
-                    # the grad-input kernel is persistent: leave a few SMs for the NCCL kernel that is in flight
-                    lib.sinc_set_reserved_sms(_SYNC_RESERVED_SMS)
-                    try:
-                        launch(True, False)
-                    finally:
-                        lib.sinc_set_reserved_sms(0)
+                    # the grad-input kernel is persistent: it leaves a few SMs to the NCCL kernel that is in flight
+                    # (a per-call option of the C ABI, not a process-wide setting)
+                    used |= launch(True, False, reserved_sms=_SYNC_RESERVED_SMS)
                 work.wait()
                 if average:
                     gp /= torch.distributed.get_world_size(group)
             else:
-                launch(need_x, need_p)
+                used |= launch(need_x, need_p)
+            if debug is not None:
+                eng = _lib.decode_engines(used)
+                if need_x:
+                    debug["bwd_input"] = eng["bwd_input"]
+                if need_p:
+                    debug["bwd_filter"] = eng["bwd_filter"]
         if gfilt is not None:
-            SincConvFunction._last_grad_filters = gfilt
-        g_low = gp[0] if need_p and ctx.needs_input_grad[1] else None
-        g_band = gp[1] if need_p and ctx.needs_input_grad[2] else None
-        return gx, g_low, g_band, None, None, None, None, None, None, None
+            debug["grad_filters"] = gfilt
+        x_dt, low_dt, band_dt = ctx.in_dtypes
+        g_low = gp[0].to(low_dt) if need_p and ctx.needs_input_grad[1] else None
+        g_band = gp[1].to(band_dt) if need_p and ctx.needs_input_grad[2] else None
+        if gx is not None and x_dt != torch.float32:
+            gx = gx.to(x_dt)
+        return gx, g_low, g_band, None, None, None, None, None, None, None, None, None
 
 
 class SincConv1d(nn.Module):
@@ -216,13 +275,21 @@ class SincConv1d(nn.Module):
     and ``(batch, out_channels, samples)`` output as the reference ``agents.perception.SincConv1d``
     (agents/perception.py:23-118), so state_dicts load in both directions.
 
-    Extra keyword-only argument ``out_dtype`` (float32 default, or bfloat16): storage type of the output
-    activation; the arithmetic is fp32 either way.
+    Extra keyword-only arguments: ``out_dtype`` (float32 default, or bfloat16): storage type of the output
+    activation, the arithmetic is fp32 either way; ``engine`` ('auto' | 'fma' | 'tc' | 'tc_tf32' | None = package
+    default): kernel family, passed to the C ABI with every call.
+
+    A module cast with ``.double()`` / ``.bfloat16()`` / ``.half()`` accepts inputs of that dtype and returns that
+    dtype like the reference's does; its state is read at the stored values and the arithmetic stays fp32.
     """
 
     def __init__(self, out_channels, kernel_size, sample_rate=None, min_low_hz=50, min_band_hz=50,
-                 *, out_dtype=torch.float32):
+                 *, out_dtype=torch.float32, engine=None):
         super().__init__()
+        if engine is not None and engine not in _lib.ENGINE_CODES:
+            raise ValueError(f"engine must be one of {sorted(_lib.ENGINE_CODES)} or None (package default)")
+        self.engine = engine          # None = package default (set_engine); travels with every call as a per-call option
+        self._debug = None            # per-instance debug channel, see capture()
         self.out_channels = out_channels
         self.kernel_size = kernel_size + 1 if kernel_size % 2 == 0 else kernel_size  # odd taps only
         self.sample_rate = sample_rate or _default_sample_rate()
@@ -266,16 +333,44 @@ class SincConv1d(nn.Module):
                                    f"(channels, samples) and needs 1 channel, got {tuple(waveform.shape)}")
             waveform = waveform.unsqueeze(0)
             unbatched = True
+        pdt = self.low_hz_.dtype
+        autocast = torch.is_autocast_enabled("cuda")
+        if not autocast:
+            _check_input(waveform, pdt)
+        # a cast module (.double() / .bfloat16() / .half()): same dtype in, same dtype out, fp32 arithmetic in between
+        out_dtype = self.out_dtype if pdt == torch.float32 else torch.float32
         needs_graph = torch.is_grad_enabled() and (waveform.requires_grad or self.low_hz_.requires_grad
                                                    or self.band_hz_.requires_grad)
-        if needs_graph or torch.is_autocast_enabled("cuda"):
-            y = SincConvFunction.apply(waveform, self.low_hz_, self.band_hz_, self.window, self.n_,
-                                       self.sample_rate, self.min_low_hz, self.min_band_hz, self.out_dtype,
-                                       getattr(self, "_grad_sync", None))
-        else:  # inference: straight to the C ABI, no autograd node
-            y, _ = _forward_impl(waveform, self.low_hz_, self.band_hz_, self.window, self.n_, self.sample_rate,
-                                 self.min_low_hz, self.min_band_hz, self.out_dtype)
+        with torch.cuda.nvtx.range("sinc_forward") if _NVTX else _null_ctx:
+            if needs_graph or autocast:
+                y = SincConvFunction.apply(waveform, self.low_hz_, self.band_hz_, self.window, self.n_,
+                                           self.sample_rate, self.min_low_hz, self.min_band_hz, out_dtype,
+                                           getattr(self, "_grad_sync", None), self.engine, self._debug)
+            else:  # inference: straight to the C ABI, no autograd node
+                y, _ = _forward_impl(waveform if pdt == torch.float32 else waveform.float(), self.low_hz_, self.band_hz_,
+                                     self.window, self.n_, self.sample_rate, self.min_low_hz, self.min_band_hz, out_dtype,
+                                     self.engine, self._debug)
+        if pdt != torch.float32 and not autocast:
+            y = y.to(pdt)
         return y.squeeze(0) if unbatched else y
+
+    @contextlib.contextmanager
+    def capture(self, grad_filters=False, phase_stamps=False):
+        """Debug channel of THIS instance (tests, bench): inside the block every forward/backward through the module
+        records which engine ran each pass ('fwd', 'bwd_input', 'bwd_filter' -> 'fma' | 'tc_tf32' | 'tc16') into the
+        yielded dict; with grad_filters=True the backward also leaves the intermediate (C,K) dL/dw there
+        ('grad_filters'); with phase_stamps=True the 16-bit tcgen05 kernels write their entry / post-prologue / exit
+        time stamps into a device buffer ('phase_stamps', 20 int64, layout: include/sinc_b200.h)."""
+        rec = {}
+        if grad_filters:
+            rec["want_grad_filters"] = True
+        if phase_stamps:
+            rec["phase_stamps"] = torch.zeros(20, dtype=torch.int64, device=self.low_hz_.device)
+        previous, self._debug = self._debug, rec
+        try:
+            yield rec
+        finally:
+            self._debug = previous
 
     def enable_grad_sync(self, group=None, average=False):
         """Data-parallel use WITHOUT DistributedDataParallel: all-reduce (SUM, or mean) the 2*out_channels

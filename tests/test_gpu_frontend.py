@@ -18,7 +18,8 @@ def dev():
     return torch.device("cuda:0")
 
 
-@pytest.mark.parametrize("B,C,G,T", [(2, 64, 8, 4096), (3, 16, 8, 100), (1, 64, 8, 48000), (2, 24, 3, 8192 + 4), (4, 8, 1, 8)])
+@pytest.mark.parametrize("B,C,G,T", [(2, 64, 8, 4096), (3, 16, 8, 100), (1, 64, 8, 48000), (2, 24, 3, 8192 + 4), (4, 8, 1, 8),
+                                     (2, 64, 8, 4099), (3, 16, 2, 16385), (2, 8, 8, 1)])   # ragged lengths: 4-byte path
 def test_fused_groupnorm_gelu_vs_torch(B, C, G, T):
     gen = torch.Generator().manual_seed(B * 100 + T)
     ref = nn.GroupNorm(G, C)
@@ -86,9 +87,15 @@ def test_sinc_frontend_unfused_fallback_and_state_dict():
     keys = set(fe.state_dict().keys())
     assert keys == {"sinc_conv.low_hz_", "sinc_conv.band_hz_", "sinc_conv.window", "sinc_conv.n_",
                     "sinc_norm.weight", "sinc_norm.bias"}       # the slice of PerceptionAgent's state_dict
-    x = torch.randn(2, 4098, device=dev())                       # T % 4 != 0: FMA forward; GroupNorm kernels refuse
+    # T % 4 != 0 (the reference's gelu(GroupNorm(conv)) takes any length): unfused conv + the 4-byte GroupNorm path
+    gen = torch.Generator().manual_seed(3)
+    xr = torch.randn(2, 1, 4098, generator=gen)
+    orc = O.OracleSincConv1d(64, 251, sample_rate=8000).double()
+    gn = nn.GroupNorm(8, 64).double()
+    z64 = F.gelu(gn(orc(xr.double()))).detach()
+    assert max_rel(fe(xr.to(dev())).cpu(), z64) <= 2e-5
     with pytest.raises(RuntimeError):
-        fe(x)
+        fe(torch.randn(2, 1, 0, device=dev()))                   # empty input: the same rule as SincConv1d
     x = torch.randn(2, 4096, device=dev())
     sb.set_engine("fma")
     try:

@@ -89,11 +89,24 @@ def test_abi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(build.LIB_PATH)
     for sym in declared:
         assert hasattr(lib, sym), sym
+    # hardware probes / micro-benchmarks live in their own library; the product library must not export them
+    build.build_diag_library()
+    dheader = open(os.path.join(ROOT, "include", "sinc_b200_diag.h")).read()
+    ddeclared = set(re.findall(r"\b(sinc_[a-z_0-9]+)\s*\(", dheader.split('extern "C" {', 1)[1]))
+    assert ddeclared == set(_lib.DIAG_SYMBOLS), ddeclared ^ set(_lib.DIAG_SYMBOLS)
+    dlib = ctypes.CDLL(build.DIAG_LIB_PATH)
+    for sym in ddeclared:
+        assert hasattr(dlib, sym), sym
+        assert not hasattr(lib, sym), f"{sym} is a diagnostic: it must not be exported from libsinc_b200.so"
+    # no process-wide setters in the ABI (per-call sinc_options instead)
+    for gone in ("sinc_set_engine", "sinc_get_engine", "sinc_set_reserved_sms", "sinc_last_engine_mask", "sinc_tc_status",
+                 "sinc_tc_phase_stamps"):
+        assert not hasattr(lib, gone), gone
 
 
 def test_abi_non_compute_calls():
     lib = _lib.load()
-    assert lib.sinc_abi_version() == 1
+    assert lib.sinc_abi_version() == 2
     assert lib.sinc_strerror(0) == b"success"
     assert b"NULL" in lib.sinc_strerror(-1)
     assert b"odd K" in lib.sinc_strerror(-2)
@@ -101,18 +114,21 @@ def test_abi_non_compute_calls():
     # the workspace also holds the self-validating filter table (header + W[64][256]) behind the partial tiles
     assert lib.sinc_workspace_bytes(1, 1, 4, 3) >= 4096 + 64 * 256 * 4
     assert lib.sinc_workspace_bytes(1, 1, 70, 300) > lib.sinc_workspace_bytes(1, 1, 64, 251)
-    assert lib.sinc_set_engine(7) == -8
-    assert lib.sinc_set_engine(0) == 0 and lib.sinc_get_engine() == 0
     for code, name in enumerate(("auto", "fma", "tc", "tc_tf32")):      # every engine name the package accepts
         sb.set_engine(name)
-        assert lib.sinc_get_engine() == code
+        assert sb.get_engine() == name and _lib.ENGINE_CODES[name] == code
+    with pytest.raises(ValueError):
+        sb.set_engine("cpu")
     sb.set_engine("auto")
+    with pytest.raises(ValueError):
+        sb.SincConv1d(4, 9, engine="cpu")
+    assert sb.SincConv1d(4, 9, engine="fma").engine == "fma"
     # argument validation happens before any CUDA call
     fb = _lib.FilterBank()
-    assert lib.sinc_forward(ctypes.byref(fb), None, 0, None, 0, 1, 1, None, 0, None) == -1
+    assert lib.sinc_forward(ctypes.byref(fb), None, 0, None, 0, 1, 1, None, 0, None, None) == -1
     fb.low_hz = fb.band_hz = fb.window = fb.n = 16
     fb.C, fb.K = 4, 4
-    assert lib.sinc_forward(ctypes.byref(fb), None, 0, None, 0, 1, 1, None, 0, None) == -2   # even K
+    assert lib.sinc_forward(ctypes.byref(fb), None, 0, None, 0, 1, 1, None, 0, None, None) == -2   # even K
 
 
 def test_shard_rows_partitions_the_batch():
@@ -148,8 +164,9 @@ def test_allreduce_filter_grads_world_size_2_gloo():
 
 
 def test_bench_reference_arm_runs_on_cpu_and_ours_refuses_without_a_gpu():
-    """`bench.py --impl reference` (the oracle port timed on the host cores) prints the contract's JSON line; our own
-    arm has no CPU fallback and must say so instead of printing a number."""
+    """`bench.py --impl reference` (the staged reference module -- or the oracle port when baseline/_ref is absent --
+    timed on the host cores) prints the contract's JSON line with the same `config` keys as our arm; our own arm has no
+    CPU fallback and must say so instead of printing a number."""
     import json
     import subprocess
     import sys
@@ -159,7 +176,11 @@ def test_bench_reference_arm_runs_on_cpu_and_ours_refuses_without_a_gpu():
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads([l for l in p.stdout.splitlines() if l.startswith("{")][-1])
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "audio-s/s"
-    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    staged = os.path.exists(os.path.join(ROOT, "baseline", "_ref", "reference", "agents", "perception.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if staged else "port") and line["e2e"]["h2d_bytes_per_step"] == 0
+    sys.path.insert(0, ROOT)
+    import bench as bench_module
+    assert line["config"] == bench_module.workload_config("cfg1_b1_t16000_fwd", 1)    # what our arm prints as `config`
     if not torch.cuda.is_available():
         q = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
         assert q.returncode != 0 and "no CPU fallback" in (q.stdout + q.stderr)

@@ -29,13 +29,13 @@ def main():
         nbytes = lib.sinc_workspace_bytes(B, T, C, K)
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         fns = {
-            "fwd": lambda: lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), 0, B, T, P(ws), nbytes, stream),
+            "fwd": lambda: lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), 0, B, T, P(ws), nbytes, stream, None),
             "bwd_input": lambda: lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, P(gx), None, None, None, B, T,
-                                                   P(ws), nbytes, stream),
+                                                   P(ws), nbytes, stream, None),
             "bwd_filter": lambda: lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, None, P(gp[0]), P(gp[1]), None,
-                                                    B, T, P(ws), nbytes, stream),
+                                                    B, T, P(ws), nbytes, stream, None),
             "bwd_both": lambda: lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, P(gx), P(gp[0]), P(gp[1]), None,
-                                                  B, T, P(ws), nbytes, stream),
+                                                  B, T, P(ws), nbytes, stream, None),
         }
         for name, fn in fns.items():
             for _ in range(3):

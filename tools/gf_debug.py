@@ -5,7 +5,6 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import sinc_oracle as O
 import sincformer_metacog_speech_enhancement_b200 as sb
-from sincformer_metacog_speech_enhancement_b200.sinc import SincConvFunction
 dev = torch.device("cuda:0")
 orc = O.OracleSincConv1d(64, 251, sample_rate=16000)
 import json
@@ -21,10 +20,9 @@ for (B, T, need_x) in CFG:
     for rep in range(REPS):
         xd = x.to(dev).requires_grad_(bool(need_x))
         dut.low_hz_.grad = dut.band_hz_.grad = None
-        SincConvFunction._expose_grad_filters = True
-        y = dut(xd); y.backward(g.to(dev)); torch.cuda.synchronize()
-        SincConvFunction._expose_grad_filters = False
-        G = SincConvFunction._last_grad_filters.cpu().double().reshape(64, 251)
+        with dut.capture(grad_filters=True) as rec:
+            y = dut(xd); y.backward(g.to(dev)); torch.cuda.synchronize()
+        G = rec["grad_filters"].cpu().double().reshape(64, 251)
         E = (G - R).abs().max(1).values / R.abs().max()
         bad = [(c, round(float(E[c]) * 1e5, 1)) for c in range(64) if E[c] > 5e-5]
         res.append((round(float(E.max()) * 1e5, 2), bad))

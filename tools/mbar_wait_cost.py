@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from sincformer_metacog_speech_enhancement_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_diag()
 lib.sinc_mbar_wait_cost.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
 names = {0: "try_wait + suspend hint", 1: "try_wait", 2: "test_wait", 3: "tc::mbar_wait"}
 for mode in (0, 1, 2, 3):

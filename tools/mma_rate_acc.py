@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from sincformer_metacog_speech_enhancement_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_diag()
 dev = torch.device("cuda:0")
 names = {1: "one accumulator", 2: "alternating every MMA", 3: "runs of three per accumulator"}
 for N in (32, 64):

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from sincformer_metacog_speech_enhancement_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_diag()
 dev = torch.device("cuda:0")
 for N in (32, 64, 112):
     for k in (0, 1, 2, 4):

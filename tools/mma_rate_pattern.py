@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from sincformer_metacog_speech_enhancement_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_diag()
 dev = torch.device("cuda:0")
 for N in (112, 64, 32, 16):
     for pattern in (0, 1, 2):

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 from sincformer_metacog_speech_enhancement_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_diag()
 dev = torch.device("cuda:0")
 names = {0: "idle", 1: "tcgen05.st", 2: "LDS.128", 3: "tcgen05.ld"}
 for N in (32, 64, 112):

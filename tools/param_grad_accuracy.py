@@ -5,7 +5,6 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch
 import sinc_oracle as O
 import sincformer_metacog_speech_enhancement_b200 as sb
-from sincformer_metacog_speech_enhancement_b200.sinc import SincConvFunction
 
 B, T = int(sys.argv[1]) if len(sys.argv) > 1 else 8, int(sys.argv[2]) if len(sys.argv) > 2 else 48000
 torch.manual_seed(0)
@@ -20,21 +19,19 @@ for eng in ("fma", "tc_tf32", "tc"):
     sb.set_engine(eng)
     dut = sb.SincConv1d(64, 251, sample_rate=16000).to(dev)
     xd = x.to(dev).requires_grad_(True)
-    SincConvFunction._expose_grad_filters = True
-    y = dut(xd); y.backward(g.to(dev)); torch.cuda.synchronize()
-    SincConvFunction._expose_grad_filters = False
+    with dut.capture(grad_filters=True) as rec:
+        y = dut(xd); y.backward(g.to(dev)); torch.cuda.synchronize()
     out = {"y": mr(y.detach().cpu(), o64["y"]), "gx": mr(xd.grad.cpu(), o64["gx"]),
-           "gfilt": mr(SincConvFunction._last_grad_filters.cpu(), o64["gfilt"]),
+           "gfilt": mr(rec["grad_filters"].cpu(), o64["gfilt"]),
            "g_low": mr(dut.low_hz_.grad.cpu(), o64["g_low"]), "g_band": mr(dut.band_hz_.grad.cpu(), o64["g_band"])}
     print(json.dumps({eng: out}))
 sb.set_engine("auto")
 if len(sys.argv) > 3:
     sb.set_engine(sys.argv[3])
     dut = sb.SincConv1d(64, 251, sample_rate=16000).to(dev)
-    SincConvFunction._expose_grad_filters = True
-    y = dut(x.to(dev)); y.backward(g.to(dev)); torch.cuda.synchronize()
-    SincConvFunction._expose_grad_filters = False
-    G = SincConvFunction._last_grad_filters.cpu().double().reshape(64, 251); R = o64["gfilt"].double().reshape(64, 251)
+    with dut.capture(grad_filters=True) as rec:
+        y = dut(x.to(dev)); y.backward(g.to(dev)); torch.cuda.synchronize()
+    G = rec["grad_filters"].cpu().double().reshape(64, 251); R = o64["gfilt"].double().reshape(64, 251)
     E = (G - R).abs() / R.abs().max()
     print("err by tap mod 8:", [float(E[:, r::8].max()) for r in range(8)])
     print("err by filter (first 8):", [float(E[c].max()) for c in range(8)], "max over filters", float(E.max(1).values.max()), "min", float(E.max(1).values.min()))

@@ -17,14 +17,16 @@ x = torch.randn(B, 1, T, device=dev); y = torch.empty(B, C, T, device=dev); g = 
 gx = torch.empty(B, 1, T, device=dev); gp = torch.empty(2, C, device=dev)
 nbytes = lib.sinc_workspace_bytes(B, T, C, K); ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
 st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+stamps = torch.zeros(20, dtype=torch.int64, device=dev)
+opt = _lib.Options(); opt.phase_stamps = stamps.data_ptr()     # per-call diagnostic option of the C ABI
 def step():
-    assert lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), 0, B, T, P(ws), nbytes, st) == 0
-    assert lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, P(gx), P(gp[0]), P(gp[1]), None, B, T, P(ws), nbytes, st) == 0
+    assert lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), 0, B, T, P(ws), nbytes, st, ctypes.byref(opt)) == 0
+    assert lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), 0, P(gx), P(gp[0]), P(gp[1]), None, B, T, P(ws), nbytes, st,
+                             ctypes.byref(opt)) == 0
 for _ in range(200):     # ~90 ms of sustained load before the stamps that count
     step()
 torch.cuda.synchronize()
-out = (ctypes.c_longlong * 20)()
-assert lib.sinc_tc_phase_stamps(out) == 0
+out = stamps.cpu().tolist()
 print(json.dumps({"grad_input_filters_from_table": int(out[18])}))
 for k, name in enumerate(("fwd", "bwd_input", "bwd_filter")):
     c0, t0, c1, t1, c2, t2 = out[6 * k: 6 * k + 6]

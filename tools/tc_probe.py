@@ -65,7 +65,7 @@ def kmajor_image(mat, lbo, sbo):
 def run(case):
     import torch
     from sincformer_metacog_speech_enhancement_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_diag()
     rng = np.random.default_rng(0)
     M = 128
     ri = lambda *s: rng.integers(-4, 5, size=s).astype(np.float32)
