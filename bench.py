@@ -352,6 +352,98 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = world * audio_per_step / (ms_step * 1e-3)
 
+    # --- per-kernel timings through the C ABI (rank 0, N == 1 only), right after the headline: the same thermal state ---
+    extra = {}
+    if rank == 0 and world == 1:
+        fb = _bank(m.low_hz_.detach(), m.band_hz_.detach(), m.window, m.n_, m.sample_rate, m.min_low_hz, m.min_band_hz)
+        nbytes = lib.sinc_workspace_bytes(B, T, C, K)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        y = torch.empty(B, C, T, dtype=out_dtype, device=dev)
+        gx = torch.empty(B, 1, T, device=dev)
+        gp = torch.empty(2, C, device=dev)
+        code = _lib.DTYPE_BF16 if dt == "bf16" else _lib.DTYPE_F32
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        used = ctypes.c_int32(0)
+        opt = _lib.Options()
+        opt.engine = _lib.ENGINE_CODES[args.engine]
+        opt.engines_used = ctypes.pointer(used)
+        O = ctypes.byref(opt)
+
+        def k_fwd():
+            _lib.check(lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), code, B, T, P(ws), nbytes, stream, O), "fwd")
+
+        def k_bwd_input():
+            _lib.check(lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), code, P(gx), None, None, None, B, T,
+                                         P(ws), nbytes, stream, O), "bwd_input")
+
+        def k_bwd_filter():
+            _lib.check(lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), code, None, P(gp[0]), P(gp[1]), None, B, T,
+                                         P(ws), nbytes, stream, O), "bwd_filter")
+
+        esize = 2 if dt == "bf16" else 4
+        n = B * T
+        kern = {}
+        for name, fn, flops, byts in (
+                ("fwd", k_fwd, FLOP_FWD * n, n * (4 + C * esize)),
+                ("bwd_input", k_bwd_input, FLOP_FWD * n, n * (C * esize + 4)),
+                ("bwd_filter+finalize", k_bwd_filter, FLOP_FWD * n, n * (C * esize + 4))):
+            ms = timed(fn, max(3, args.steps // 2), 3) / max(3, args.steps // 2)
+            eng = _lib.decode_engines(used.value)[{"bwd_filter+finalize": "bwd_filter"}.get(name, name)]
+            kern[name] = {"ms": ms, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6, "engine": eng}
+        extra["kernels"] = kern
+        dom = max(kern, key=lambda k: kern[k]["ms"])
+        # Roofline of the dominant kernel.  The contraction is compute-bound on every pipe (184 FLOP/B, SURVEY F5).
+        # FMA engine: FP32 pipe, nominal 148 SM x 128 lanes x 2 x clocks.max.sm (not in MEASURED_PEAKS).
+        # tcgen05 engines: an algorithmic product costs `mmas` tensor-core instructions -- 3 with fp32 activations
+        # (hi*hi + hi*lo + lo*hi); 2 in the backward kernels with bf16 activations (grad_y is exact in one bf16 piece);
+        # the forward always splits both operands (3) -- so the ceiling for ALGORITHMIC flops is the measured dense
+        # bf16 rate / mmas (kind::f16 operands) or / 2 / 3 (kind::tf32 operands).  `frac_of_raw_bf16` is the same
+        # achieved number against the measured dense bf16 rate itself.
+        sm_max = clocks.get("sm_max_mhz") or 1965.0
+
+        def peak_of(name, eng):
+            if eng == "tc16":
+                mmas = 2 if (dt == "bf16" and name != "fwd") else 3
+                return peaks["bf16_tflops"] / mmas, "tensor", (
+                    f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / {mmas} (16-bit split operands: "
+                    f"{mmas} kind::f16 MMAs per algorithmic product)")
+            if eng == "tc_tf32":
+                return peaks["bf16_tflops"] / 2 / 3, "tensor", (f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / 2 (tf32) "
+                                                               "/ 3 (3xTF32 split)")
+            return 148 * 128 * 2 * sm_max * 1e6 / 1e12, "fp32_fma", (f"nominal 148 SM x 128 FMA lanes x 2 x {sm_max:.0f} MHz "
+                                                                     "(FP32 pipe is not in MEASURED_PEAKS)")
+        for k in kern:
+            kern[k]["frac_of_pipe_peak"] = kern[k]["tflops"] / peak_of(k, kern[k]["engine"])[0]
+            kern[k]["frac_of_raw_bf16"] = kern[k]["tflops"] / peaks["bf16_tflops"]
+        peak, bound, peak_src = peak_of(dom, kern[dom]["engine"])
+        # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py)
+        traffic = None
+        for rnd in (ROUND, "r01"):
+            try:
+                with open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json")) as fh:
+                    tr = json.load(fh)
+                kname = {"fwd": "fwd", "bwd_input": "bwd_input", "bwd_filter+finalize": "bwd_filter"}[dom] + \
+                        {"tc16": "_tc16_kernel", "tc_tf32": "_tc_kernel", "fma": "_fma_kernel"}[kern[dom]["engine"]]
+                if args.workload == "cfg2_b32_t48000_fp32" and kname in tr:
+                    traffic = tr[kname]["dram_bytes"]
+                    break
+            except Exception:
+                continue
+        alg_flops = FLOP_PER_SAMPLE * n / ms_step / 1e9
+        extra["roofline"] = {"kernel": dom, "bound": bound, "achieved": kern[dom]["tflops"], "peak": peak,
+                            "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak,
+                            "frac_of_raw_bf16": kern[dom]["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
+                            "peak_source": peak_src,
+                            "hbm": {"achieved_gbs": kern[dom]["gbs"], "peak_gbs": peaks["hbm_gbs"],
+                                    "frac": kern[dom]["gbs"] / peaks["hbm_gbs"]},
+                            "step": {"algorithmic_tflops": alg_flops,
+                                     "frac_of_split_adjusted_burst": alg_flops / (peaks["bf16_tflops"] / 3),
+                                     "frac_of_split_adjusted_sustained": alg_flops / (peaks["bf16_tflops_sustained"] / 3),
+                                     "frac_of_raw_bf16": alg_flops / peaks["bf16_tflops"],
+                                     "algorithmic_gbs": (BYTES_PER_SAMPLE_F32 if dt == "fp32" else BYTES_PER_SAMPLE_BF16) * n / ms_step / 1e6}}
+
+
     # --- e2e: module API, pinned host input -> H2D, D2H of grad-input and parameter grads ---------------
     # A training loop's input pipeline: the H2D copy of step k+1 and the D2H read-back of step k-1 run while step k
     # computes -- on TWO copy streams (the GPU has separate copy engines per direction; one stream would serialise the
@@ -462,6 +554,7 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    line.update(extra)
 
     # --- sustained: the same step >= 2000 times back to back (the SM clock settles under tensor + HBM load) ---------
     if args.sustained > 0:
@@ -536,96 +629,8 @@ def run_ours(args):
         line["cfg5"] = strong("cfg5", 64, 960000, torch.bfloat16, False)
         torch.cuda.empty_cache()
 
-    # --- per-kernel timings through the C ABI (rank 0, N == 1 only) -------------------------------------
+    # --- baseline legs (rank 0, N == 1 only) ---------------------------------------------------------------------
     if rank == 0 and world == 1:
-        fb = _bank(m.low_hz_.detach(), m.band_hz_.detach(), m.window, m.n_, m.sample_rate, m.min_low_hz, m.min_band_hz)
-        nbytes = lib.sinc_workspace_bytes(B, T, C, K)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        y = torch.empty(B, C, T, dtype=out_dtype, device=dev)
-        gx = torch.empty(B, 1, T, device=dev)
-        gp = torch.empty(2, C, device=dev)
-        code = _lib.DTYPE_BF16 if dt == "bf16" else _lib.DTYPE_F32
-        P = lambda t: ctypes.c_void_p(t.data_ptr())
-        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        used = ctypes.c_int32(0)
-        opt = _lib.Options()
-        opt.engine = _lib.ENGINE_CODES[args.engine]
-        opt.engines_used = ctypes.pointer(used)
-        O = ctypes.byref(opt)
-
-        def k_fwd():
-            _lib.check(lib.sinc_forward(ctypes.byref(fb), P(x), T, P(y), code, B, T, P(ws), nbytes, stream, O), "fwd")
-
-        def k_bwd_input():
-            _lib.check(lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), code, P(gx), None, None, None, B, T,
-                                         P(ws), nbytes, stream, O), "bwd_input")
-
-        def k_bwd_filter():
-            _lib.check(lib.sinc_backward(ctypes.byref(fb), P(x), T, P(g), code, None, P(gp[0]), P(gp[1]), None, B, T,
-                                         P(ws), nbytes, stream, O), "bwd_filter")
-
-        esize = 2 if dt == "bf16" else 4
-        n = B * T
-        kern = {}
-        for name, fn, flops, byts in (
-                ("fwd", k_fwd, FLOP_FWD * n, n * (4 + C * esize)),
-                ("bwd_input", k_bwd_input, FLOP_FWD * n, n * (C * esize + 4)),
-                ("bwd_filter+finalize", k_bwd_filter, FLOP_FWD * n, n * (C * esize + 4))):
-            ms = timed(fn, max(3, args.steps // 2), 3) / max(3, args.steps // 2)
-            eng = _lib.decode_engines(used.value)[{"bwd_filter+finalize": "bwd_filter"}.get(name, name)]
-            kern[name] = {"ms": ms, "tflops": flops / ms / 1e9, "gbs": byts / ms / 1e6, "engine": eng}
-        line["kernels"] = kern
-        dom = max(kern, key=lambda k: kern[k]["ms"])
-        # Roofline of the dominant kernel.  The contraction is compute-bound on every pipe (184 FLOP/B, SURVEY F5).
-        # FMA engine: FP32 pipe, nominal 148 SM x 128 lanes x 2 x clocks.max.sm (not in MEASURED_PEAKS).
-        # tcgen05 engines: an algorithmic product costs `mmas` tensor-core instructions -- 3 with fp32 activations
-        # (hi*hi + hi*lo + lo*hi); 2 in the backward kernels with bf16 activations (grad_y is exact in one bf16 piece);
-        # the forward always splits both operands (3) -- so the ceiling for ALGORITHMIC flops is the measured dense
-        # bf16 rate / mmas (kind::f16 operands) or / 2 / 3 (kind::tf32 operands).  `frac_of_raw_bf16` is the same
-        # achieved number against the measured dense bf16 rate itself.
-        sm_max = clocks.get("sm_max_mhz") or 1965.0
-
-        def peak_of(name, eng):
-            if eng == "tc16":
-                mmas = 2 if (dt == "bf16" and name != "fwd") else 3
-                return peaks["bf16_tflops"] / mmas, "tensor", (
-                    f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / {mmas} (16-bit split operands: "
-                    f"{mmas} kind::f16 MMAs per algorithmic product)")
-            if eng == "tc_tf32":
-                return peaks["bf16_tflops"] / 2 / 3, "tensor", (f"MEASURED_PEAKS bf16 {peaks['bf16_tflops']} TF/s ({peaks['source']}) / 2 (tf32) "
-                                                               "/ 3 (3xTF32 split)")
-            return 148 * 128 * 2 * sm_max * 1e6 / 1e12, "fp32_fma", (f"nominal 148 SM x 128 FMA lanes x 2 x {sm_max:.0f} MHz "
-                                                                     "(FP32 pipe is not in MEASURED_PEAKS)")
-        for k in kern:
-            kern[k]["frac_of_pipe_peak"] = kern[k]["tflops"] / peak_of(k, kern[k]["engine"])[0]
-            kern[k]["frac_of_raw_bf16"] = kern[k]["tflops"] / peaks["bf16_tflops"]
-        peak, bound, peak_src = peak_of(dom, kern[dom]["engine"])
-        # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (tools/ncu_traffic.py)
-        traffic = None
-        for rnd in (ROUND, "r01"):
-            try:
-                with open(os.path.join(ROOT, "profiles", f"{rnd}_traffic.json")) as fh:
-                    tr = json.load(fh)
-                kname = {"fwd": "fwd", "bwd_input": "bwd_input", "bwd_filter+finalize": "bwd_filter"}[dom] + \
-                        {"tc16": "_tc16_kernel", "tc_tf32": "_tc_kernel", "fma": "_fma_kernel"}[kern[dom]["engine"]]
-                if args.workload == "cfg2_b32_t48000_fp32" and kname in tr:
-                    traffic = tr[kname]["dram_bytes"]
-                    break
-            except Exception:
-                continue
-        alg_flops = FLOP_PER_SAMPLE * n / ms_step / 1e9
-        line["roofline"] = {"kernel": dom, "bound": bound, "achieved": kern[dom]["tflops"], "peak": peak,
-                            "unit": "TFLOP/s", "frac": kern[dom]["tflops"] / peak,
-                            "frac_of_raw_bf16": kern[dom]["tflops"] / peaks["bf16_tflops"], "traffic": traffic,
-                            "peak_source": peak_src,
-                            "hbm": {"achieved_gbs": kern[dom]["gbs"], "peak_gbs": peaks["hbm_gbs"],
-                                    "frac": kern[dom]["gbs"] / peaks["hbm_gbs"]},
-                            "step": {"algorithmic_tflops": alg_flops,
-                                     "frac_of_split_adjusted_burst": alg_flops / (peaks["bf16_tflops"] / 3),
-                                     "frac_of_split_adjusted_sustained": alg_flops / (peaks["bf16_tflops_sustained"] / 3),
-                                     "frac_of_raw_bf16": alg_flops / peaks["bf16_tflops"],
-                                     "algorithmic_gbs": (BYTES_PER_SAMPLE_F32 if dt == "fp32" else BYTES_PER_SAMPLE_BF16) * n / ms_step / 1e6}}
-
         # --- gpu_reference: the reference's own torch ops through cuDNN on this GPU (the practical GPU bar) ---------
         if not args.no_gpu_ref and dt == "fp32":
             try:

@@ -135,12 +135,12 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
 /* ---- next row N1: the GroupNorm(8, C) + GELU that follows the layer -----------------
  * Replaces agents/perception.py:233-234 (the GroupNorm module `sinc_norm` = nn.GroupNorm(8, C) of :157 applied to
  * the layer output, then F.gelu) with streaming kernels that touch the (B,C,T) activation as few times as possible.  fp32; any T
- * 16-byte aligned tensors.
+ * (16-byte accesses when T % 4 == 0 and the tensors are 16-byte aligned, 4-byte accesses otherwise).
  *
  * sinc_forward_gn: sinc_forward (fp32 y) that also emits, from the convolution epilogue, the partial sums the
  *   GroupNorm statistics need: gn_partial is float2 [B][C/8][sinc_forward_gn_partials(T)] = (sum y, sum y^2) per
  *   utterance, group of 8 filters and output tile.  SINC_E_ENGINE if the 16-bit tensor-core forward cannot take the
- *   shape (C % 8 != 0, K > 265, T % 4 != 0) -- then use sinc_forward + sinc_gn_stats.
+ *   shape (C % 8 != 0, K > 265) -- then use sinc_forward + sinc_gn_stats.
  * sinc_gn_stats: one read pass over y -> float2 partial [B*C][sinc_gn_chunks(T)].
  * sinc_gn_gelu_forward: z = gelu(gamma_c * (y - mean) * rstd + beta_c); `partial` holds, per group, rows_per_group
  *   rows of np pairs (rows_per_group = C/G, np = sinc_gn_chunks(T) after sinc_gn_stats; rows_per_group = 1,

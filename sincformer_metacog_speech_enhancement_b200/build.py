@@ -26,6 +26,9 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr", "-extended-lambda",
     "-Xcompiler", "-fPIC", "-shared",
 ]
+# experiment builds only (e.g. SINC_EXTRA_NVCC_FLAGS=-DSINC_ABLATION for tools/ablate.py): part of the digest, so a
+# library built with extra flags is never mistaken for the product build
+NVCC_FLAGS += os.environ.get("SINC_EXTRA_NVCC_FLAGS", "").split()
 
 
 def sources() -> list[str]:

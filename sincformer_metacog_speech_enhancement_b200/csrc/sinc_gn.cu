@@ -122,7 +122,9 @@ gn_apply_gelu_kernel(const float* __restrict__ y, const float2* __restrict__ par
                 mean, rstd);
   const int chunk = blockIdx.y;
   if (chunk == 0 && c == g * cpg && threadIdx.x == 0) stats[b * G + g] = make_float2(mean, rstd);
-  const float a = __ldg(gamma + c) * rstd, sh = __ldg(beta + c) - mean * a;  // u = a*y + sh
+  // u = a * (y - mean) + beta: the subtraction first -- a*y + (beta - mean*a) cancels when the group's variance is tiny
+  // (rstd ~ 1/sqrt(eps)); the kernel is HBM-bound, the extra FADD is free
+  const float a = __ldg(gamma + c) * rstd, sh = __ldg(beta + c);
   const int64_t t0 = (int64_t)chunk * GN_CHUNK;
   const int64_t n = (T - t0) < GN_CHUNK ? (T - t0) : GN_CHUNK;
   if constexpr (V) {
@@ -132,17 +134,17 @@ gn_apply_gelu_kernel(const float* __restrict__ y, const float2* __restrict__ par
     for (int i = threadIdx.x; i < n / 4; i += GN_THREADS) {
       const float4 v = __ldg(p + i);
       float4 r;
-      r.x = gelu_f(fmaf(a, v.x, sh));
-      r.y = gelu_f(fmaf(a, v.y, sh));
-      r.z = gelu_f(fmaf(a, v.z, sh));
-      r.w = gelu_f(fmaf(a, v.w, sh));
+      r.x = gelu_f(fmaf(a, v.x - mean, sh));
+      r.y = gelu_f(fmaf(a, v.y - mean, sh));
+      r.z = gelu_f(fmaf(a, v.z - mean, sh));
+      r.w = gelu_f(fmaf(a, v.w - mean, sh));
       o[i] = r;
     }
   } else {
     const float* p = y + row * T + t0;
     float* o = z + row * T + t0;
 #pragma unroll 4
-    for (int i = threadIdx.x; i < n; i += GN_THREADS) o[i] = gelu_f(fmaf(a, __ldg(p + i), sh));
+    for (int i = threadIdx.x; i < n; i += GN_THREADS) o[i] = gelu_f(fmaf(a, __ldg(p + i) - mean, sh));
   }
 }
 

@@ -113,6 +113,23 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
       : "memory");
 }
 
+// kind::f16 instruction descriptor bits 13 / 14: negate the A / B operand on the way into the multiplier
+constexpr uint32_t kIdescNegA = 1u << 13, kIdescNegB = 1u << 14;
+
+// fp32 pair -> packed bf16 pairs (v1 in the high half): hi = RN(v), nmid = RN(hi - v) = -RN(v - hi), i.e. the NEGATED
+// second piece.  Four instructions per pair -- F2FP, two mixed-precision FHADD.BF16 (sub.rn.f32.bf16 takes the packed
+// halves directly), F2FP -- instead of six (the plain form needs a shift and a mask to widen hi before the two
+// subtractions).  The MMA that consumes the piece sets the negate bit of that operand in its instruction descriptor,
+// so the sign costs nothing.
+__device__ __forceinline__ void split_bf16x2_negmid(float v0, float v1, uint32_t& hi, uint32_t& nmid) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(v1), "f"(v0));
+  float n0, n1;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tsub.rn.f32.bf16 %0, lo, %3;\n\tsub.rn.f32.bf16 %1, hi, %4;\n\t}\n"
+      : "=f"(n0), "=f"(n1)
+      : "r"(hi), "f"(v0), "f"(v1));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(nmid) : "f"(n1), "f"(n0));
+}
+
 // ---- TMEM <-> registers: 32 lanes x 32 bit, 8 consecutive columns per call ---------------------------
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -149,6 +166,17 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
+}
+// 32 consecutive columns per call: one MIO instruction instead of four (the MMA issuers share that queue)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 

@@ -15,13 +15,21 @@
 // with SBO = 128 is a plain row-pitch-16-byte matrix, so the e = 1 half of K is the same memory read one row
 // earlier (start address - 16 bytes): no duplication, no im2col.  Shared memory holds no filters at all.
 //
-// col2im (per epilogue warp: 32 tap pairs x 32 positions from tcgen05.ld, cell (L, j) belongs to output 2L + j):
-//   store   lane L = 16h + a writes its 32 values to S[h*545 + 34a + j]           (32 conflict-free STS)
-//   gather  lane r reads S[h*545 + 32m + r], m = 0..16: the cell is (a = m, j = r - 2m), output r, when 2m <= r,
-//           and (a = m-1, j = r - 2m + 34), output r + 32, when 2m >= r + 3 -- two mask FMAs per load
-// i.e. 66 shared-memory wavefronts per 1024 accumulator values (the 3xTF32 kernel spends 96 on half as many
-// MMA flops per value).  Sums are carried across the two 32-column chunks in registers, the eight warps'
-// 128-cell windows and the carry from earlier stages are combined in a fixed order: bitwise reproducible.
+// col2im (per epilogue warp: 32 tap pairs L x 64 positions c of the accumulator; cell (L, c) belongs to window cell
+// o = c + 2L).  The accumulator is read with the 16x256b TMEM load shape: thread t = 4r + q4 receives, for the four rows
+// L = r + 8m (m = 0..3), the columns c = 8j + 2 q4 + e (j = 0..7, e = 0..1) -- rows EIGHT LANES APART land in the same
+// thread, and 2 * 8m = 16m is a multiple of the thread's column period 8, so the four rows are added in registers with
+// no cross-thread traffic at all:
+//     E[r][8 j' + 2 q4 + e] = sum_m D[r + 8m][8 (j' - 2m) + 2 q4 + e],   j' = 0..13          (36 FADD per thread)
+// leaving 8 rows x 112 columns per warp (896 values instead of 2048) for the part that must cross threads:
+//   store   thread (r, q4) writes its 14 float2 to S[r][14 + 8 j' + 2 q4]        (14 STS.64, row pitch 152: conflict free)
+//   gather  lane l sums S[r][14 + (l + 32 i) - 2r] over r = 0..7 for its four cells o = l + 32 i   (32 LDS.32; the 14-word
+//           margins on both sides of a row are zero, so no cell needs a range check)
+// i.e. 60 shared-memory wavefronts per 2048 accumulator values -- the previous version (one row per thread, 32x32b
+// loads) needed 132 and was bound by exactly that traffic (ncu r05a: LSU data pipe + MMA operand reads = 93 % of the
+// shared-memory pipe).  The fragment layout is pinned on hardware by tests/test_gpu_tc.py::test_tmem_load_16x256b_fragment.
+// The eight warps' 128-cell windows and the carry from earlier stages are combined in a fixed order: bitwise
+// reproducible.
 //
 // Pipeline: 4 producer warps (TMA tensor boxes -> registers -> bf16 hi/mid -> planes, for fp32 and bf16 grad_y alike;
 // 2-slot operand ring, the last row of a stage is also the halo row of the next), 1 MMA issuer warp
@@ -32,6 +40,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -49,22 +58,31 @@ constexpr int H2_REGS_ISSUE = 40;  // issuer warpgroup
 static_assert(3 * 128 * H2_REGS_WORK + 128 * H2_REGS_ISSUE <= H2_THREADS * 128, "setmaxnreg.inc would block forever");
 constexpr int H2_NS = 128;       // D columns (positions) per stage
 constexpr int H2_SLOTS = 2;      // B ring depth (load latency is hidden by the staging boxes, not by the ring)
+constexpr int H2_ACCS = 3;       // accumulator buffers in TMEM (128 columns each)
+constexpr int H2_TM_W = 128 * H2_ACCS;  // first TMEM column of W' (hi: 64 columns, mid: the next 64)
+static_assert(H2_TM_W + 128 <= 512, "TMEM budget");
 constexpr int H2_PLANE = (H2_NS + 1) * 16;       // bytes: halo row + 128 rows of 8 filters x bf16
 constexpr int H2_SLOT = 2 * 8 * H2_PLANE;        // hi planes [8], mid planes [8]
 constexpr int H2_WIN = 384;                      // output window of one stage: 128 positions + 2*127 + 1 (3 combiner warps x 4 cells)
 static_assert(H2_WIN == 4 * 96, "combiner cell ownership");
-constexpr int H2_SKEW = 1092;                    // floats per epilogue warp: 2 regions of 16 rows x pitch 34 (+1)
+constexpr int H2_EPITCH = 152;                   // floats per row of an epilogue warp's col2im buffer: 14 zero | 112 | 26 zero;
+                                                 // 152 = 24 mod 32: the STS.64 of a half-warp (4 rows x 8 words) hit 32 banks
+constexpr int H2_SKEW = 8 * H2_EPITCH;           // floats per epilogue warp: 8 rows
 constexpr int H2_STG_BOX = 64 * 32 * 4;                        // one TMA box: 64 filter rows x 32 positions, fp32, 128B-swizzled
 constexpr int H2_SM_STG = 0;                                   // staging: [4 producer warps][2 boxes]
-constexpr int H2_SM_G = H2_SM_STG + 4 * 2 * H2_STG_BOX;        // B ring; in the prologue: fp32 filters [64][256]
-constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // skew buffers: one per (epilogue warp, 32-column chunk)
-constexpr int H2_SM_OUT = H2_SM_S + 8 * 2 * H2_SKEW * 4;       // 2 x 8 x window [128] (double-buffered by stage parity)
+constexpr int H2_NBOX = 2;                                     // TMA boxes in flight per producer warp: 64 KB of grad_y per SM
+                                                               // (3 measured slower, r02h: 0.103 vs 0.097 ms for the bare feed)
+                                                               // (an L2 tensor prefetch six stages ahead changed nothing either)
+constexpr int H2_SM_G = H2_SM_STG + 4 * H2_NBOX * H2_STG_BOX;  // B ring; in the prologue: fp32 filters [64][256]
+constexpr int H2_SM_S = H2_SM_G + H2_SLOTS * H2_SLOT;          // col2im buffers: one per epilogue warp (margins stay zero)
+constexpr int H2_SM_OUT = H2_SM_S + 8 * H2_SKEW * 4;           // 2 x 8 x window [128] (double-buffered by stage parity)
 constexpr int H2_SM_CARRY = H2_SM_OUT + 2 * 8 * 128 * 4;       // 2 x carry [256]
 constexpr int H2_SM_BAR = H2_SM_CARRY + 2 * 256 * 4;
-constexpr int H2_SM_TOTAL = H2_SM_BAR + 256;
+constexpr int H2_SM_TOTAL = H2_SM_BAR + 512;
 static_assert(64 * 256 * 4 <= H2_SLOTS * H2_SLOT, "filter staging must fit in the B ring");
 static_assert(H2_SM_S % 16 == 0 && H2_SM_OUT % 16 == 0 && H2_SM_G % 1024 == 0, "alignment");
 static_assert(H2_SM_TOTAL + 1024 <= 227 * 1024, "shared memory budget");
+static_assert(21 + 4 * H2_NBOX <= 64, "barrier table");
 
 struct BwdInputTc16Args {
   Bank bank;
@@ -75,7 +93,17 @@ struct BwdInputTc16Args {
   int64_t nblocks;         // B * blocks_per_row
   long long* phase;        // diagnostic time stamps (CTA 0), may be null
   const uint8_t* tab;      // filter table left in the workspace by the grad-filter kernel (sinc_synth.cuh), or nullptr
+#ifdef SINC_ABLATION
+  int ablate;              // ablation build only (tools/ablate.py): bit 0 epilogue skips col2im, 1 epilogue skips the TMEM
+                           // load too, 2 producers skip conversion + plane stores, 3 producers skip the staging reads too,
+                           // 4 the issuer issues no MMAs (commits only).  Results are garbage by construction.
+#endif
 };
+#ifdef SINC_ABLATION
+#define ABL(bit) ((a.ablate >> (bit)) & 1)
+#else
+#define ABL(bit) 0
+#endif
 
 // v0, v1 -> packed bf16 pairs (v1 in the high half): hi = RN(v), mid = RN(v - hi)
 __device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& mid) {
@@ -96,12 +124,12 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + H2_SM_BAR);
   uint64_t* b_full = bars;         // [4]  producers (4 warps) -> issuers
   uint64_t* b_empty = bars + 4;    // [4]  issuer (1 commit per stage) -> producers
-  uint64_t* d_full = bars + 8;     // [2 buffers][2 column halves]  issuer -> epilogue
-  uint64_t* d_empty = bars + 12;   // [2][2]  epilogue (4 warps) -> issuer
+  uint64_t* d_full = bars + 8;     // [H2_ACCS accumulator buffers]  issuer -> epilogue
+  uint64_t* d_empty = bars + 12;   // [H2_ACCS]  epilogue (8 warps) -> issuer
   uint64_t* win_full = bars + 16;  // [2]  epilogue (8 warps) -> combiners: the windows of a stage are written
   uint64_t* win_empty = bars + 18; // [2]  combiners (3 warps) -> epilogue: the window buffer may be rewritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  uint64_t* st_full = bars + 21;   // [4 producer warps][2]  TMA -> the warp that issued it
+  uint64_t* st_full = bars + 21;   // [4 producer warps][H2_NBOX]  TMA -> the warp that issued it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.bank.C, K = a.bank.K, H = (K - 1) / 2;
@@ -119,13 +147,13 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
       tc::mbar_init(&b_full[i], 4);
       tc::mbar_init(&b_empty[i], 1);
       tc::mbar_init(&d_full[i], 1);
-      tc::mbar_init(&d_empty[i], 4);
+      tc::mbar_init(&d_empty[i], 8);
     }
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&win_full[i], 8);
       tc::mbar_init(&win_empty[i], 3);
     }
-    for (int i = 0; i < 8; ++i) tc::mbar_init(&st_full[i], 1);
+    for (int i = 0; i < 4 * H2_NBOX; ++i) tc::mbar_init(&st_full[i], 1);
     tc::tensormap_prefetch(&gmap);
     tc::mbar_init_fence();
   }
@@ -175,7 +203,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  // TMEM map: [0,256) two accumulators of 128 columns; [256,320) W' hi, [320,384) W' mid (column = e*32 + c/2)
+  // TMEM map: [0,384) THREE accumulators of 128 columns; [384,448) W' hi, [448,512) W' mid (column = e*32 + c/2).
+  // Three, not two: the accumulator of stage s is free again when the epilogue has read it out of TMEM, which takes
+  // longer than the MMAs of one stage (a barrier wake-up on each side of 64 KB of tcgen05.ld); with two buffers the
+  // issuer waited for that every stage (r02e: 2500 cycles per stage against 1536 of MMAs).
   if (warp < 4) {
     const float* wst = reinterpret_cast<const float*>(ring);
     const int kp = 32 * warp + lane;  // tap pair = TMEM lane
@@ -194,8 +225,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
           const int ca = 8 * cq + ((2 * (j & 3) + rot) & 7), cb = 8 * cq + ((2 * (j & 3) + 1 + rot) & 7);
           split_bf16x2(wst[ca * 256 + 2 * kp + e], wst[cb * 256 + 2 * kp + e], hi[j], mid[j]);
         }
-        tc::tmem_st8(tmem + lane_base + 256 + 32 * e + 8 * cg, hi);
-        tc::tmem_st8(tmem + lane_base + 320 + 32 * e + 8 * cg, mid);
+        tc::tmem_st8(tmem + lane_base + H2_TM_W + 32 * e + 8 * cg, hi);
+        tc::tmem_st8(tmem + lane_base + H2_TM_W + 64 + 32 * e + 8 * cg, mid);
       }
     }
     tc::tmem_st_wait();
@@ -252,9 +283,9 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
     const int pg = GB ? ((lane >> 2) & 1) | (((lane >> 2) & 2) << 1) | (((lane >> 2) & 4) >> 1) : lane >> 2;
     constexpr int BOXB = GB ? H2_STG_BOX / 2 : H2_STG_BOX;   // bytes of one box: 64 rows x 32 positions
     const int n0 = 32 * pw + 4 * pg;          // first of this thread's four columns within the stage
-    const uint32_t stg0 = tc::smem_addr(smem + H2_SM_STG + pw * 2 * H2_STG_BOX);
-    uint64_t* my_full = st_full + 2 * pw;
-    uint32_t ldq = 0;                                // boxes consumed so far by this warp (box = ldq & 1)
+    const uint32_t stg0 = tc::smem_addr(smem + H2_SM_STG + pw * H2_NBOX * H2_STG_BOX);
+    uint64_t* my_full = st_full + H2_NBOX * pw;
+    uint32_t ldq = 0;                                // boxes consumed so far by this warp (box = ldq % H2_NBOX)
     const bool keeps_halo = (pw == 3 && pg == 7);    // these lanes convert the last row of every stage
     uint4 hsave[2], msave[2];                        // ... which is also row 0 (the halo row) of the next stage's slot
     hsave[0] = hsave[1] = msave[0] = msave[1] = make_uint4(0u, 0u, 0u, 0u);
@@ -264,22 +295,24 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
       constexpr int ESZ = GB ? 2 : 4;
       const uint8_t* gb = reinterpret_cast<const uint8_t*>(a.g) + (b * C) * T * ESZ;
       gvec vv[16];
-      auto issue_box = [&](int i, uint32_t q) {  // stage i of this run -> box q & 1 (the whole warp calls; one lane issues)
+      auto issue_box = [&](int i, uint32_t q) {  // stage i of this run -> box q % H2_NBOX (the whole warp calls; one lane issues)
         if (tc::elect_one()) {
-          uint64_t* bar = &my_full[q & 1];
+          uint64_t* bar = &my_full[q % H2_NBOX];
           tc::mbar_expect_tx(bar, BOXB);
-          tc::tensor_load_3d(stg0 + (q & 1) * H2_STG_BOX, &gmap, (int)(c0 + (int64_t)H2_NS * i + 32 * pw), 0, (int)b, bar);
+          tc::tensor_load_3d(stg0 + (q % H2_NBOX) * H2_STG_BOX, &gmap, (int)(c0 + (int64_t)H2_NS * i + 32 * pw), 0, (int)b, bar);
         }
         __syncwarp();
       };
-      issue_box(0, ldq);
-      if (nst > 1) issue_box(1, ldq + 1);
+#pragma unroll
+      for (int pre = 0; pre < H2_NBOX; ++pre)
+        if (pre < nst) issue_box(pre, ldq + pre);
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
         const int slot = (int)(sg & 1);
         {
-          ok = ok && tc::mbar_wait(&my_full[ldq & 1], (ldq >> 1) & 1);
-          const uint32_t box = stg0 + (ldq & 1) * H2_STG_BOX;
+          ok = ok && tc::mbar_wait(&my_full[ldq % H2_NBOX], (ldq / H2_NBOX) & 1);
+          const uint32_t box = stg0 + (ldq % H2_NBOX) * H2_STG_BOX;
+          if (!ABL(3))
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int cq = fg + 4 * (j >> 3);
@@ -299,8 +332,46 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
             }
           }
           __syncwarp();
-          if (i + 2 < nst) issue_box(i + 2, ldq + 2);  // same box: its contents are in registers now
+          if (i + H2_NBOX < nst) issue_box(i + H2_NBOX, ldq + H2_NBOX);  // same box: its contents are in registers now
           ++ldq;
+        }
+        // Convert FIRST, wait for the slot afterwards: the slot becomes free when the MMAs of stage sg - 2 complete, and
+        // from that moment the issuer is waiting for this stage -- with the conversion (64 pairs per thread) behind the
+        // wait, ring slot hand-over was a ping-pong with ~800 cycles of conversion in its critical path (ncu r02c: the
+        // issuer polled b_full 7 times per stage, the producers b_empty twice, tensor pipe 53 % active).  Now only the
+        // sixteen 16-byte stores, the proxy fence and the arrive follow the wait.
+        uint4 hq[2][4], mq[2][4];
+        if (ABL(2)) {
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int o = 0; o < 4; ++o) hq[s2][o] = mq[s2][o] = make_uint4(0u, 0u, 0u, 0u);
+        } else
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const gvec* v8 = vv + 8 * s2;
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            uint4 h, m;
+            if constexpr (GB) {
+              // bf16 inputs: pick the 16-bit sample o of two filter rows and pack them (even filter in the low half)
+              auto pk = [&](const uint2& lo, const uint2& hi2) {
+                const uint32_t wl = o < 2 ? lo.x : lo.y, wh = o < 2 ? hi2.x : hi2.y;
+                return __byte_perm(wl, wh, (o & 1) ? 0x7632 : 0x5410);
+              };
+              h = make_uint4(pk(v8[0], v8[1]), pk(v8[2], v8[3]), pk(v8[4], v8[5]), pk(v8[6], v8[7]));
+              m = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+              auto comp = [&](const float4& f) { return o == 0 ? f.x : o == 1 ? f.y : o == 2 ? f.z : f.w; };
+              // mid planes hold the NEGATED second piece (4 instead of 6 instructions per pair); its MMA negates B back
+              tc::split_bf16x2_negmid(comp(v8[0]), comp(v8[1]), h.x, m.x);
+              tc::split_bf16x2_negmid(comp(v8[2]), comp(v8[3]), h.y, m.y);
+              tc::split_bf16x2_negmid(comp(v8[4]), comp(v8[5]), h.z, m.z);
+              tc::split_bf16x2_negmid(comp(v8[6]), comp(v8[7]), h.w, m.w);
+            }
+            hq[s2][o] = h;
+            mq[s2][o] = m;
+          }
         }
         // slot sg & 1 was last read by the MMAs of stage sg - 2
         if (sg >= 2) ok = ok && tc::mbar_wait(&b_empty[slot], (uint32_t)(((sg - 2) >> 1) & 1));
@@ -309,10 +380,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
           if (pw == 0) {  // run start: the halo row (position c0 - 1) has no previous stage; lane = filter pair
             const int64_t p = c0 - 1;
             const bool in = p >= 0 && p < T;
-            const int hq = lane >> 2;                                                      // plane
-            const int hrot = GB ? (hq & 3) : 2 * (hq & 3);
-            const int hc = 8 * hq + ((2 * (lane & 3) + hrot) & 7);       // the pair of filters of this word (see W')
-            const int hc1 = 8 * hq + ((2 * (lane & 3) + 1 + hrot) & 7);
+            const int hq8 = lane >> 2;                                                     // plane
+            const int hrot = GB ? (hq8 & 3) : 2 * (hq8 & 3);
+            const int hc = 8 * hq8 + ((2 * (lane & 3) + hrot) & 7);      // the pair of filters of this word (see W')
+            const int hc1 = 8 * hq8 + ((2 * (lane & 3) + 1 + hrot) & 7);
             uint32_t h, m;
             if constexpr (GB) {
               const uint16_t* g16 = reinterpret_cast<const uint16_t*>(gb);
@@ -324,10 +395,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
               const float* g32 = reinterpret_cast<const float*>(gb);
               const float w0 = (in && hc < C) ? __ldg(g32 + (int64_t)hc * T + p) : 0.f;
               const float w1 = (in && hc1 < C) ? __ldg(g32 + (int64_t)hc1 * T + p) : 0.f;
-              split_bf16x2(w0, w1, h, m);
+              tc::split_bf16x2_negmid(w0, w1, h, m);
             }
-            *reinterpret_cast<uint32_t*>(base + hq * H2_PLANE + (lane & 3) * 4) = h;
-            if constexpr (!GB) *reinterpret_cast<uint32_t*>(base + (8 + hq) * H2_PLANE + (lane & 3) * 4) = m;
+            *reinterpret_cast<uint32_t*>(base + hq8 * H2_PLANE + (lane & 3) * 4) = h;
+            if constexpr (!GB) *reinterpret_cast<uint32_t*>(base + (8 + hq8) * H2_PLANE + (lane & 3) * 4) = m;
           }
         } else if (keeps_halo) {
 #pragma unroll
@@ -339,37 +410,19 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
             }
           }
         }
+        if (!ABL(2))
 #pragma unroll
         for (int s2 = 0; s2 < 2; ++s2) {
           const int cq = fg + 4 * s2;
           if (cq < 2 * ncb) {
-            const gvec* v8 = vv + 8 * s2;
 #pragma unroll
             for (int o = 0; o < 4; ++o) {
-              uint4 h, m;
-              if constexpr (GB) {
-                // bf16 inputs: pick the 16-bit sample o of two filter rows and pack them (even filter in the low half)
-                auto pk = [&](const uint2& lo, const uint2& hi2) {
-                  const uint32_t wl = o < 2 ? lo.x : lo.y, wh = o < 2 ? hi2.x : hi2.y;
-                  return __byte_perm(wl, wh, (o & 1) ? 0x7632 : 0x5410);
-                };
-                h = make_uint4(pk(v8[0], v8[1]), pk(v8[2], v8[3]), pk(v8[4], v8[5]), pk(v8[6], v8[7]));
-                m = make_uint4(0u, 0u, 0u, 0u);
-              } else {
-                auto comp = [&](const float4& f) { return o == 0 ? f.x : o == 1 ? f.y : o == 2 ? f.z : f.w; };
-                split_bf16x2(comp(v8[0]), comp(v8[1]), h.x, m.x);
-                split_bf16x2(comp(v8[2]), comp(v8[3]), h.y, m.y);
-                split_bf16x2(comp(v8[4]), comp(v8[5]), h.z, m.z);
-                split_bf16x2(comp(v8[6]), comp(v8[7]), h.w, m.w);
-              }
               uint8_t* dst = base + cq * H2_PLANE + (n0 + o + 1) * 16;
-              *reinterpret_cast<uint4*>(dst) = h;
-              if constexpr (!GB) *reinterpret_cast<uint4*>(dst + 8 * H2_PLANE) = m;
-              if (o == 3) {
-                hsave[s2] = h;
-                msave[s2] = m;
-              }
+              *reinterpret_cast<uint4*>(dst) = hq[s2][o];
+              if constexpr (!GB) *reinterpret_cast<uint4*>(dst + 8 * H2_PLANE) = mq[s2][o];
             }
+            hsave[s2] = hq[s2][3];
+            msave[s2] = mq[s2][3];
           }
         }
         tc::fence_async_smem();
@@ -429,38 +482,44 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
         const int stg0 = tc::uniform((int)(stage & 0x3fffffff));  // only bits 0..1 of the stage counter matter below
         const uint32_t tm = tc::uniform((int)tmem);
         const uint32_t ring0 = tc::uniform((int)tc::smem_addr(ring));
-        const uint32_t idesc = tc::make_idesc_f16(128, 64, tc::kFmtBF16, tc::kFmtBF16);
+        // One N = 128 MMA per (tap parity, 16 filters, product): 24 instructions of 64 tensor-pipe cycles per stage.  The
+        // earlier version issued the two 64-column halves of a stage separately (48 MMAs of 32 cycles) so that the
+        // epilogue of half 0 could start early -- but one thread sustains an MMA only every ~40 cycles in this loop
+        // (descriptor arithmetic on the uniform datapath + MIO back-pressure from the other warps' shared-memory and
+        // TMEM traffic; ncu r02c: the UTCHMMA instructions stall on `mio`, tensor pipe 53 % active), so 32-cycle MMAs
+        // left the pipe idle a third of the time.  The accumulators are double-buffered by stage, so the epilogue of
+        // stage s still overlaps the MMAs of stage s + 1.
+        const uint32_t idesc = tc::make_idesc_f16(128, H2_NS, tc::kFmtBF16, tc::kFmtBF16);
+        const uint32_t idesc_nb = idesc | tc::kIdescNegB;          // the mid planes of grad_y are stored negated (producers)
         const uint64_t bdesc = tc::make_smem_desc(H2_PLANE, 128);  // K chunk stride = plane, 8-row groups contiguous
         for (int i = 0; i < nstu; ++i) {
           const int sg = stg0 + i;
-          const int slot = sg & 1, buf = sg & 1;
+          const int slot = sg & 1;
+          const int acb = sg % H2_ACCS, acp = (sg / H2_ACCS) & 1;   // accumulator buffer and the parity of its use count
+          ok = ok && tc::mbar_wait(&d_empty[acb], (uint32_t)(acp ^ 1));
           ok = ok && tc::mbar_wait(&b_full[slot], (uint32_t)((sg >> 1) & 1));
-#pragma unroll 1
-          for (int hf = 0; hf < 2; ++hf) {
-            ok = ok && tc::mbar_wait(&d_empty[2 * buf + hf], (uint32_t)(((sg >> 1) & 1) ^ 1));
-            tc::fence_after_sync();
-            const uint32_t d = tm + 128 * buf + 64 * hf;
-            const uint32_t sbase = ring0 + slot * H2_SLOT + hf * 64 * 16;
-            if (tc::elect_one()) {
-              uint32_t acc = 0;
-              for (int e = 0; e < 2; ++e) {
-                uint32_t ah = tm + 256 + 32 * e;
-                uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
-                for (int cb = 0; cb < ncbu; ++cb) {
-                  const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
-                  tc::mma_f16_ts(d, ah, dh, idesc, acc);
-                  if constexpr (!GB) tc::mma_f16_ts(d, ah, dm, idesc, 1);  // bf16 grad_y has no mid planes
-                  tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
-                  acc = 1;
-                  ah += 8;
-                  bh += 2 * H2_PLANE;
-                }
+          tc::fence_after_sync();
+          const uint32_t d = tm + 128 * acb;
+          const uint32_t sbase = ring0 + slot * H2_SLOT;
+          if (tc::elect_one()) {
+            uint32_t acc = 0;
+            for (int e = 0; e < (ABL(4) ? 0 : 2); ++e) {
+              uint32_t ah = tm + H2_TM_W + 32 * e;
+              uint32_t bh = sbase + (1 - e) * 16;  // e = 0 reads rows 1..128, e = 1 the same planes one row earlier
+              for (int cb = 0; cb < ncbu; ++cb) {
+                const uint64_t dh = tc::desc_at(bdesc, bh), dm = tc::desc_at(bdesc, bh + 8 * H2_PLANE);
+                tc::mma_f16_ts(d, ah, dh, idesc, acc);
+                if constexpr (!GB) tc::mma_f16_ts(d, ah, dm, idesc_nb, 1);  // bf16 grad_y has no mid planes
+                tc::mma_f16_ts(d, ah + 64, dh, idesc, 1);
+                acc = 1;
+                ah += 8;
+                bh += 2 * H2_PLANE;
               }
-              if (hf == 1) tc::mma_commit(&b_empty[slot]);
-              tc::mma_commit(&d_full[2 * buf + hf]);
             }
-            __syncwarp();
+            tc::mma_commit(&b_empty[slot]);
+            tc::mma_commit(&d_full[acb]);
           }
+          __syncwarp();
         }
       }
       __syncwarp();
@@ -471,54 +530,62 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
       // ------------- epilogue: TMEM -> skewed column sums -> window -> gx --------------------------------------
       const int q = warp & 3, hf = warp >> 2;
       const uint32_t lane_base = (uint32_t)(32 * q) << 16;
-      float* S0 = skew + warp * (2 * H2_SKEW);  // chunk 0 (columns 0..31 of this warp's half), chunk 1 follows
-      float* srow = S0 + (lane >> 4) * 545 + (lane & 15) * 34;
-      float m0[17], m1[17];
-#pragma unroll
-      for (int m = 0; m < 17; ++m) {
-        m0[m] = (2 * m <= lane) ? 1.f : 0.f;
-        m1[m] = (2 * m >= lane + 3) ? 1.f : 0.f;
-      }
+      float* S0 = skew + warp * H2_SKEW;                                 // [8][H2_EPITCH], margins zero since the prologue
+      float* srow = S0 + (lane >> 2) * H2_EPITCH + 14 + 2 * (lane & 3);   // thread (r, q4): row r, first column pair
+      const float* gat = S0 + 14 + lane;                                 // lane l gathers cells o = l + 32 i
       for (int i = 0; i < nst; ++i) {
         const int64_t sg = stage + i;
         const int buf = (int)(sg & 1);
-        ok = ok && tc::mbar_wait(&d_full[2 * buf + hf], (uint32_t)((sg >> 1) & 1));
+        const int acb = (int)(sg % H2_ACCS);
+        ok = ok && tc::mbar_wait(&d_full[acb], (uint32_t)((sg / H2_ACCS) & 1));
         tc::fence_after_sync();
-        uint32_t va[32], vb[32];
-        tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf, va);
-        tc::tmem_ld32(tmem + lane_base + 128 * buf + 64 * hf + 32, vb);
-        tc::tmem_ld_wait();
+        uint32_t va[32], vb[32];   // va: TMEM lanes 0..15 of this quarter (rows r, r+8), vb: lanes 16..31 (rows r+16, r+24)
+        const uint32_t dcol = tmem + lane_base + 128 * acb + 64 * hf;
+        if (!ABL(1)) {
+          tc::tmem_ld16x256_x8(dcol, va);
+          tc::tmem_ld16x256_x8(dcol + (16u << 16), vb);
+          tc::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int z = 0; z < 32; ++z) va[z] = vb[z] = 0u;
+        }
         tc::fence_before_sync();  // all 64 columns of this half have left TMEM: release the accumulator
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&d_empty[2 * buf + hf]);
+        if (lane == 0) tc::mbar_arrive(&d_empty[acb]);
+        // rows r + 8m, m = 0..3: element (j, e) of row m is v[4j + 2(m & 1) + e] of va (m < 2) or vb; it belongs to column
+        // group j' = j + 2m of the summed row
+        float c0s = 0.f, c1s = 0.f, c2s = 0.f, c3s = 0.f;
+        if (!ABL(0)) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          srow[j] = __uint_as_float(va[j]);
-          srow[H2_SKEW + j] = __uint_as_float(vb[j]);
+        for (int jp = 0; jp < 14; ++jp) {
+          float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            const int j = jp - 2 * m;
+            if (j >= 0 && j < 8) {
+              const uint32_t* v = m < 2 ? va : vb;
+              e0 += __uint_as_float(v[4 * j + 2 * (m & 1)]);
+              e1 += __uint_as_float(v[4 * j + 2 * (m & 1) + 1]);
+            }
+          }
+          *reinterpret_cast<float2*>(srow + 8 * jp) = make_float2(e0, e1);
         }
         __syncwarp();
-        float a00 = 0.f, a01 = 0.f, a10 = 0.f, a11 = 0.f, b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-        const float* col = S0 + lane;
 #pragma unroll
-        for (int m = 0; m < 17; ++m) {
-          const float u0 = col[32 * m], u1 = col[545 + 32 * m];
-          const float w0 = col[H2_SKEW + 32 * m], w1 = col[H2_SKEW + 545 + 32 * m];
-          a00 = fmaf(u0, m0[m], a00);
-          a01 = fmaf(u0, m1[m], a01);
-          a10 = fmaf(u1, m0[m], a10);
-          a11 = fmaf(u1, m1[m], a11);
-          b00 = fmaf(w0, m0[m], b00);
-          b01 = fmaf(w0, m1[m], b01);
-          b10 = fmaf(w1, m0[m], b10);
-          b11 = fmaf(w1, m1[m], b11);
+        for (int r = 0; r < 8; ++r) {
+          const float* row = gat + r * H2_EPITCH - 2 * r;
+          c0s += row[0];
+          c1s += row[32];
+          c2s += row[64];
+          c3s += row[96];
         }
-        // chunk 0 covers window cells [0,96): a00 | a01 + a10 | a11; chunk 1 the same 32 cells later
+        }
         ok = ok && tc::mbar_wait(&win_empty[buf], (uint32_t)(((sg >> 1) & 1) ^ 1));  // combined two stages ago
         float* win = outw + buf * (8 * 128) + warp * 128;
-        win[lane] = a00;
-        win[32 + lane] = (a01 + a10) + b00;
-        win[64 + lane] = a11 + (b01 + b10);
-        win[96 + lane] = b11;
+        win[lane] = c0s;
+        win[32 + lane] = c1s;
+        win[64 + lane] = c2s;
+        win[96 + lane] = c3s;
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&win_full[buf]);
       }
@@ -587,6 +654,9 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   a.nblocks = B * a.blocks_per_row;
   a.phase = phase ? phase + 6 : nullptr;  // sinc_options.phase_stamps (diagnostic, normally null)
   a.tab = filter_table;
+#ifdef SINC_ABLATION
+  a.ablate = getenv("SINC_ABLATE_BI") ? atoi(getenv("SINC_ABLATE_BI")) : 0;
+#endif
   int sms = di.sm_count - reserved_sms;  // data-parallel: a few SMs stay free for the all-reduce in flight
   if (sms < 1) sms = 1;
   const int grid = (int)(a.nblocks < sms ? a.nblocks : sms);

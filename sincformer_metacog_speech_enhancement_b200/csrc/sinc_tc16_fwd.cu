@@ -22,10 +22,13 @@
 //
 // Warp roles (352 threads): warps 0-7 epilogue (two per TMEM lane quarter, 56 columns each: TMEM -> scale ->
 // phase-interleaved staging -> 1-D bulk stores of 3.5 KB rows; plain global stores straight from the registers were
-// measured and are slower: main loop 158k -> 182k cycles), warp 8 MMA issuer (warp-uniform issue loop), warp 9
-// waveform producer (global -> max -> scale -> fp16 hi/lo -> smem), warp 10 idle after the prologue.
+// measured and are slower: main loop 158k -> 182k cycles), warp 8 MMA issuer (warp-uniform issue loop), warps 9 and 10
+// waveform producers (global -> max -> scale -> fp16 hi/lo -> smem; one per tile buffer).
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <type_traits>
 
 #include "sinc_internal.h"
 #include "sinc_synth.cuh"
@@ -33,7 +36,7 @@
 
 namespace sinc {
 
-constexpr int U_THREADS = 352;  // warps 0-7 epilogue (lane quarter = w%4, column half = w/4), 8 MMA issuer, 9 waveform producer
+constexpr int U_THREADS = 352;  // warps 0-7 epilogue (lane quarter = w%4, column half = w/4), 8 MMA issuer, 9-10 waveform producers
 constexpr int U_FB = 16;                  // filters per CTA
 constexpr int U_NJ = 112;                 // MMA N: output groups of 8 samples per tile
 constexpr int U_TT = 8 * U_NJ;            // 896 output samples per tile
@@ -64,7 +67,16 @@ struct FwdTc16Args {
   int64_t ntiles;      // B * tiles_per_row (per filter block)
   float2* gn_partial;  // optional (next row N1): per (utterance, group of 8 filters, tile) sums of y and y^2 for the
                        // GroupNorm that follows the layer (agents/perception.py:233), [B][C/8][tiles_per_row]
+#ifdef SINC_ABLATION
+  int ablate;          // ablation build only: bit 0 epilogue skips TMEM load + staging writes, 1 no stores to y, 2 no MMAs,
+                       // 3 producers skip loads + conversion
+#endif
 };
+#ifdef SINC_ABLATION
+#define FABL(bit) ((a.ablate >> (bit)) & 1)
+#else
+#define FABL(bit) 0
+#endif
 
 // power-of-two scale that puts `m` (>= 0) into [2^13, 2^14): returns the exponent, clamped so that both the
 // scale and its inverse are normal floats; m = 0 or non-finite -> 0
@@ -87,7 +99,11 @@ __device__ __forceinline__ void u_split_f16(float v, uint16_t& hi, uint16_t& lo)
   lo = __half_as_ushort(l);
 }
 
-template <bool OB, bool GN>
+// RG ("ragged"): T is not a multiple of 4 (fp32) / 8 (bf16) or y is not 16-byte aligned, so the rows of y do not start
+// on 16-byte boundaries and bulk stores cannot write them.  The staged tile then goes out with plain coalesced stores
+// from all eight epilogue warps (measured ~15 % slower than the bulk path for this kernel -- against 9x for the FMA
+// engine, which used to take every such length).
+template <bool OB, bool GN, bool RG>
 __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Args a) {
   constexpr int ESZ = OB ? 2 : 4;                 // bytes per output element
   constexpr int PITCHB = U_PITCH * ESZ;           // staging row pitch in bytes (32 resp. 16 mod 128: conflict free)
@@ -188,11 +204,14 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
     a.phase[3] = (long long)tc::global_timer_ns();
   }
 
-  if (warp == 9) {
-    // ---------------- producer: waveform tile -> max -> scale -> fp16 hi / lo in shared memory ---------------
-    // The loads of tile it+1 are issued before tile it is converted, so their L2/DRAM latency overlaps the
-    // conversion and the wait for the buffer instead of sitting in front of every tile.
+  if (warp == 9 || warp == 10) {
+    // ---------------- producers: waveform tile -> max -> scale -> fp16 hi / lo in shared memory ---------------
+    // TWO warps, one per tile buffer (warp 9 the even tiles, warp 10 the odd ones); each issues the loads of its NEXT
+    // tile (two tiles ahead) before it converts the current one.  With a single producer looking one tile ahead the
+    // issuer polled x_full 38 times per tile (ncu r02c): the waveform is read cold from DRAM while the kernel streams
+    // 3 TB/s of output into the same memory system, and one tile of MMAs (1.8 us) does not cover that latency.
     constexpr int NV = (U_XT + 31) / 32;
+    const int pb = warp - 9;                       // this producer's buffer = tile parity
     float v[NV], vn[NV];
     auto load_tile = [&](float (&dst)[NV], int64_t it) {
       const int64_t tile = slot + it * per_blk;
@@ -206,11 +225,11 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
         dst[r] = (i < U_XT && t >= 0 && t < T) ? __ldg(xr + t) : 0.f;
       }
     };
-    if (my_tiles > 0) load_tile(v, 0);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-      const int buf = (int)(it & 1);
+    if (pb < my_tiles) load_tile(v, pb);
+    for (int64_t it = pb; it < my_tiles; it += 2) {
+      const int buf = pb;
       const uint32_t par = (uint32_t)((it >> 1) & 1);
-      if (it + 1 < my_tiles) load_tile(vn, it + 1);
+      if (it + 2 < my_tiles && !FABL(3)) load_tile(vn, it + 2);
       float mx = 0.f;
 #pragma unroll
       for (int r = 0; r < NV; ++r) mx = fmaxf(mx, fabsf(v[r]));
@@ -222,6 +241,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       if (lane == 0) xinv[it & 3] = u_pow2(-se);
       uint16_t* xh = xbuf + (2 * buf) * U_XT;
       uint16_t* xl = xh + U_XT;
+      if (!FABL(3))
 #pragma unroll
       for (int r = 0; r < NV; ++r) {
         const int i = lane + 32 * r;
@@ -260,7 +280,7 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       if (tc::elect_one()) {
         uint32_t bh = xh_addr, bl = xh_addr + U_XT * 2;
         uint32_t ah = tm + U_TM_WHI, al = tm + U_TM_WLO;
-        for (int q = 0; q < nks; ++q) {
+        for (int q = 0; q < (FABL(2) ? 0 : nks); ++q) {
           const uint64_t dh = tc::desc_at(bdesc, bh), dl = tc::desc_at(bdesc, bl);
           tc::mma_f16_ts(d, ah, dh, idesc, q > 0);
           tc::mma_f16_ts(d, ah, dl, idesc, 1);
@@ -292,7 +312,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       const int64_t t0 = (tile - b * a.tiles_per_row) * U_TT;
       uint8_t* sbuf = reinterpret_cast<uint8_t*>(stage) + (int)(it % U_NSTAGE) * (U_FB * U_PITCH * 4);
       uint8_t* srow = sbuf + cl * PITCHB + (8 * col0 + r) * ESZ;
-      if (warp == 0 && lane < U_FB) tc::bulk_wait_read<U_NSTAGE - 1>();  // stores that read this buffer U_NSTAGE tiles ago
+      if constexpr (!RG)
+        if (warp == 0 && lane < U_FB) tc::bulk_wait_read<U_NSTAGE - 1>();  // stores that read this buffer U_NSTAGE tiles ago
       tc::named_bar_sync(1, 256);
       ok = ok && tc::mbar_wait(&acc_full[buf], par);
       tc::fence_after_sync();
@@ -300,13 +321,16 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
       const int64_t nvalid = T - t0 - r;       // column j is a real output iff 8j < nvalid
       const uint32_t d = tmem + lane_base + (uint32_t)(buf * U_TM_D1) + col0;
       uint32_t v[64];                          // 56 columns are this warp's; the load granule is 32
-      tc::tmem_ld32(d, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-      tc::tmem_ld32(d + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-      tc::tmem_ld_wait();
+      if (!FABL(0)) {
+        tc::tmem_ld32(d, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tc::tmem_ld32(d + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        tc::tmem_ld_wait();
+      }
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);   // accumulator may be overwritten
       float gs[4] = {0.f, 0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f};  // GroupNorm sums, 4 independent chains
+      if (!FABL(0))
 #pragma unroll
       for (int jj = 0; jj < U_NJ / 2; ++jj) {
         const float yv = __uint_as_float(v[jj]) * sc;
@@ -346,10 +370,25 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
           }
         }
       }
-      if (warp == 0 && lane < U_FB) {
+      if constexpr (RG) {
+        // plain stores: warp w writes rows 2w and 2w + 1, a 128-byte (fp32) line per instruction; the staging buffer is
+        // free again when the loop is done (the barrier at the top of the next tile orders the reuse)
+        const int n = (int)((T - t0) < U_TT ? (T - t0) : U_TT);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int row = 2 * warp + rr;
+          const int c = c0 + row;
+          if (c < C) {
+            using elem = typename std::conditional<OB, uint16_t, uint32_t>::type;
+            const elem* src = reinterpret_cast<const elem*>(sbuf + row * PITCHB);
+            elem* dst = reinterpret_cast<elem*>(a.y) + ((b * C + c) * T + t0);
+            for (int i = lane; i < n; i += 32) dst[i] = src[i];
+          }
+        }
+      } else if (warp == 0 && lane < U_FB) {
         const int row = lane;
         const int c = c0 + row;
-        if (c < C) {
+        if (c < C && !FABL(1)) {
           const int64_t n = (T - t0) < U_TT ? (T - t0) : U_TT;
           tc::bulk_store(reinterpret_cast<uint8_t*>(a.y) + ((b * C + c) * T + t0) * ESZ, sbuf + row * PITCHB,
                          (uint32_t)(n * ESZ));
@@ -357,7 +396,8 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
         tc::bulk_commit();
       }
     }
-    if (warp == 0 && lane < U_FB) tc::bulk_wait<0>();
+    if constexpr (!RG)
+      if (warp == 0 && lane < U_FB) tc::bulk_wait<0>();
   }
   (void)ok;  // mbar_wait traps on a timeout (sinc_tc.cuh): no silent failure path
   tc::fence_before_sync();
@@ -371,8 +411,13 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
 
 bool tc16_fwd_supported(int C, int K, int64_t T, const void* y, int y_dtype, const DeviceInfo& di) {
   (void)C;
-  const bool shape_ok = y_dtype == SINC_DTYPE_F32 ? T % 4 == 0 : (y_dtype == SINC_DTYPE_BF16 && T % 8 == 0);
-  return K + 7 <= U_KS && shape_ok && reinterpret_cast<uintptr_t>(y) % 16 == 0 && di.max_smem_optin >= U_SM_TOTAL + 1024;
+  (void)T;   // any length: rows that are not 16-byte aligned take the plain-store epilogue (template flag RG)
+  (void)y;
+  return K + 7 <= U_KS && (y_dtype == SINC_DTYPE_F32 || y_dtype == SINC_DTYPE_BF16) && di.max_smem_optin >= U_SM_TOTAL + 1024;
+}
+// bulk stores need every row of y to start on a 16-byte boundary and to be a multiple of 16 bytes long
+static bool fwd_rows_aligned(int64_t T, const void* y, int y_dtype) {
+  return (y_dtype == SINC_DTYPE_F32 ? T % 4 == 0 : T % 8 == 0) && reinterpret_cast<uintptr_t>(y) % 16 == 0;
 }
 
 int64_t tc16_fwd_tiles_per_row(int64_t T) { return ceil_div64(T, U_TT); }
@@ -392,13 +437,19 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
   a.ntiles = B * a.tiles_per_row;
   a.phase = phase;  // sinc_options.phase_stamps (diagnostic, normally null)
   a.gn_partial = reinterpret_cast<float2*>(gn_partial);
+#ifdef SINC_ABLATION
+  a.ablate = getenv("SINC_ABLATE_FW") ? atoi(getenv("SINC_ABLATE_FW")) : 0;
+#endif
   int64_t per_blk = di.sm_count / a.nblk;
   if (per_blk < 1) per_blk = 1;
   if (per_blk > a.ntiles) per_blk = a.ntiles;
   const int grid = (int)(per_blk * a.nblk);
   const size_t smem = U_SM_TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-  auto kern = y_dtype == SINC_DTYPE_BF16 ? fwd_tc16_kernel<true, false>
-                                         : (gn_partial ? fwd_tc16_kernel<false, true> : fwd_tc16_kernel<false, false>);
+  const bool ragged = !fwd_rows_aligned(T, y, y_dtype);
+  auto kern = y_dtype == SINC_DTYPE_BF16
+                  ? (ragged ? fwd_tc16_kernel<true, false, true> : fwd_tc16_kernel<true, false, false>)
+                  : (gn_partial ? (ragged ? fwd_tc16_kernel<false, true, true> : fwd_tc16_kernel<false, true, false>)
+                                : (ragged ? fwd_tc16_kernel<false, false, true> : fwd_tc16_kernel<false, false, false>));
   if (gn_partial && y_dtype != SINC_DTYPE_F32) return cudaErrorInvalidValue;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;

@@ -166,7 +166,7 @@ class SincFrontEnd(nn.Module):
         sc, gn = self.sinc_conv, self.sinc_norm
         C, T = sc.out_channels, waveform.shape[-1]
         engine = sc.engine or _sinc._default_engine
-        fused = (gn.num_channels // gn.num_groups == 8 and C % 8 == 0 and T % 4 == 0 and sc.kernel_size <= 265
+        fused = (gn.num_channels // gn.num_groups == 8 and C % 8 == 0 and sc.kernel_size <= 265
                  and waveform.dtype == torch.float32 and sc.low_hz_.dtype == torch.float32 and engine in ("auto", "tc"))
         if fused:
             y, partial = _SincConvWithStats.apply(waveform, sc.low_hz_, sc.band_hz_, sc.window, sc.n_, sc.sample_rate,

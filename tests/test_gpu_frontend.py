@@ -19,7 +19,7 @@ def dev():
 
 
 @pytest.mark.parametrize("B,C,G,T", [(2, 64, 8, 4096), (3, 16, 8, 100), (1, 64, 8, 48000), (2, 24, 3, 8192 + 4), (4, 8, 1, 8),
-                                     (2, 64, 8, 4099), (3, 16, 2, 16385), (2, 8, 8, 1)])   # ragged lengths: 4-byte path
+                                     (2, 64, 8, 4099), (3, 16, 2, 16385), (2, 8, 8, 5)])   # ragged lengths: 4-byte path
 def test_fused_groupnorm_gelu_vs_torch(B, C, G, T):
     gen = torch.Generator().manual_seed(B * 100 + T)
     ref = nn.GroupNorm(G, C)

@@ -112,9 +112,11 @@ def test_from_reference_on_an_existing_agent(perception):
     pa.sinc_conv = sb.SincConv1d.from_reference(ref_layer)
     pa = pa.to(dev())
     x = torch.randn(2, 1, 4000, generator=torch.Generator().manual_seed(4))
-    y_ref = ref_layer.cpu()(x).detach()
+    y_ref32 = ref_layer.cpu()(x).detach()
+    y_ref64 = copy.deepcopy(ref_layer).double()(x.double()).detach()
     y = pa.sinc_conv(x.to(dev())).cpu()
-    assert max_rel(y, y_ref) <= 1e-5
+    gap = max_rel(y_ref32, y_ref64)                  # the reference's own fp32 round-off (it synthesises in fp32)
+    assert max_rel(y, y_ref64) <= 1e-5 and max_rel(y, y_ref32) <= 1e-5 + gap
     z_real, z_imag, sigma = pa(x.to(dev()))
     assert z_real.shape == (2, 256, 250) and sigma.shape == (2, 1, 250)
 

@@ -73,7 +73,7 @@ def test_tc_forward_vs_oracle(tc_engine, C, K, sr, B, T):
     with torch.no_grad(), dut.capture() as rec:
         y = dut(x.to(dev()))
     no_trap()
-    assert rec["fwd"] == ("tc16" if tc_engine == "tc" and T % 4 == 0 and K <= 265 else "tc_tf32"), rec
+    assert rec["fwd"] == ("tc16" if tc_engine == "tc" and K <= 265 else "tc_tf32"), rec
     y32 = orc(x).detach()
     y64 = O.full_backward(orc, x, torch.zeros(B, C, T), torch.float64)["y"]
     gap = max_rel(y32, y64)
@@ -97,12 +97,38 @@ def test_tc_forward_full_size_matches_fma_engine(tc_engine):
 
 
 def test_tc_engine_refuses_unsupported_shapes(tc_engine):
-    dut = sb.SincConv1d(8, 31, sample_rate=8000).to(dev())
-    with pytest.raises(RuntimeError, match="engine"):
-        dut(torch.randn(1, 1, 4099, device=dev()))          # T % 4 != 0: rows are not 16-byte aligned
     big = sb.SincConv1d(4, 301, sample_rate=8000).to(dev())
     with pytest.raises(RuntimeError, match="engine"):
-        big(torch.randn(1, 1, 1024, device=dev()))          # K + 3 > 256
+        big(torch.randn(1, 1, 1024, device=dev()))          # K + 3 > 256: no tensor-core forward holds these taps
+    dut = sb.SincConv1d(8, 31, sample_rate=8000).to(dev())
+    x = torch.randn(1, 1, 4099, device=dev())
+    if tc_engine == "tc_tf32":
+        with pytest.raises(RuntimeError, match="engine"):
+            dut(x)                                          # 3xTF32 forward: rows must be 16-byte aligned (T % 4 == 0)
+    else:
+        with dut.capture() as rec:                          # 16-bit forward: any length (plain-store epilogue for ragged rows)
+            y = dut(x)
+        assert rec["fwd"] == "tc16"
+        orc = O.OracleSincConv1d(8, 31, sample_rate=8000)
+        assert max_rel(y.cpu(), orc(x.cpu()).detach()) <= TOL_Y
+
+
+@pytest.mark.parametrize("T", [48001, 47999, 4098, 897, 5])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_tc16_forward_ragged_lengths(T, out_dtype):
+    """Utterance lengths that are not a multiple of 4 (fp32) / 8 (bf16): the rows of y are not 16-byte aligned, the
+    16-bit tensor-core forward writes them with plain stores instead of bulk stores -- no drop to the FMA engine."""
+    orc, dut = make_pair(64, 251, 16000, out_dtype=out_dtype)
+    x = torch.randn(3, 1, T, generator=torch.Generator().manual_seed(T))
+    with torch.no_grad(), dut.capture() as rec:
+        y = dut(x.to(dev()))
+    no_trap()
+    assert rec["fwd"] == "tc16", rec
+    ref = orc(x).detach()
+    if out_dtype == torch.float32:
+        assert max_rel(y.cpu(), ref) <= TOL_Y
+    else:
+        assert bool(((y.float().cpu() - ref).abs() <= 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()).all())
 
 
 TC_BWD_SHAPES = [
