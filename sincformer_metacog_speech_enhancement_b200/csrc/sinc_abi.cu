@@ -19,7 +19,7 @@ struct Options {
 static int read_options(const sinc_options* o, Options* out) {
   if (!o) return 0;
   if (o->engine < SINC_ENGINE_AUTO || o->engine > SINC_ENGINE_TC_TF32) return SINC_E_ENGINE;
-  if (o->reserved_sms < 0 || o->reserved_sms > 64) return SINC_E_SHAPE;
+  if (o->reserved_sms < 0 || o->reserved_sms > 128) return SINC_E_SHAPE;
   if (o->phase_stamps && reinterpret_cast<uintptr_t>(o->phase_stamps) % 8) return SINC_E_ALIGN;
   out->engine = o->engine;
   out->reserved_sms = o->reserved_sms;
@@ -209,7 +209,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
     if (use_tc16)
-      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table, o.phase);
+      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table, o.phase, o.reserved_sms);
     else if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else

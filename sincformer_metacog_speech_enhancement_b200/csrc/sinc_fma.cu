@@ -534,35 +534,70 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
   double* us = dsm + K;              // [K] un-normalised taps u
   double* scratch = us + K;          // [32]
   double* part = scratch + 32;       // [FN_SPLIT][K]
+  double* chi = part + FN_SPLIT * K; // [H] n_j cos(f_hi n_j) / d_j   (the chain-rule factors: independent of G)
+  double* clo = chi + K;             // [H] n_j cos(f_lo n_j) / d_j
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
+  const bool want_params = grad_low != nullptr && grad_band != nullptr;
+  const ChanCoef cc = chan_coef(bank, c);
 
+  // The kernel is latency-bound (64 CTAs, each thread a chain of L2 loads, then fp64 sin / cos): everything that does
+  // not depend on the reduced grad-filter -- the un-normalised taps and the cosine factors of the chain rule -- is
+  // computed by the LAST warps while the others already have their partial-tile loads in flight, and the loads
+  // themselves are issued sixteen at a time (four independent fp64 chains) instead of four.
+  if (want_params && tid >= FN_THREADS - 128) {
+    for (int j = tid - (FN_THREADS - 128); j < H; j += 128) {
+      const double nj = (double)bank.n[j];
+      const double left = left_tap(cc, nj);
+      us[j] = left * (double)bank.window[j];
+      us[K - 1 - j] = left * (double)bank.window[K - 1 - j];
+      const double d = nj * 0.5 + 1e-8;
+      chi[j] = nj * cos(cc.f_hi * nj) / d;
+      clo[j] = nj * cos(cc.f_lo * nj) / d;
+    }
+    if (tid == FN_THREADS - 1) us[H] = 2.0 * (cc.f_hi - cc.f_lo) * (double)bank.window[H];
+  }
   {
     const int q = tid / (FN_THREADS / FN_SPLIT), kk = tid % (FN_THREADS / FN_SPLIT);
     for (int k = kk; k < K; k += FN_THREADS / FN_SPLIT) {
-      double s = 0.0;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;   // fixed assignment of slots to chains: bitwise reproducible
       if (layout == 0) {
         const float* p = partials + (size_t)c * Kpad + k;
+        const size_t stride = (size_t)Cpad * Kpad;
+        int sl = q;
 #pragma unroll 4
-        for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * Cpad * Kpad);
+        for (; sl + 3 * FN_SPLIT < slots; sl += 4 * FN_SPLIT) {
+          s0 += (double)__ldg(p + (size_t)sl * stride);
+          s1 += (double)__ldg(p + (size_t)(sl + FN_SPLIT) * stride);
+          s2 += (double)__ldg(p + (size_t)(sl + 2 * FN_SPLIT) * stride);
+          s3 += (double)__ldg(p + (size_t)(sl + 3 * FN_SPLIT) * stride);
+        }
+        for (; sl < slots; sl += FN_SPLIT) s0 += (double)__ldg(p + (size_t)sl * stride);
       } else if (layout == 2) {
         const int nblk = Cpad / 64;
-        const size_t slot_stride = (size_t)nblk * 128 * 128;
+        const size_t stride = (size_t)nblk * 128 * 128;
         const int h = (k >> 2) & 1, rho = k & 3, n = k >> 3;
         const float* p = partials + ((size_t)(c / 64) * 128 + 2 * (c % 64) + h) * 128 + rho * 32 + n;
+        int sl = q;
 #pragma unroll 4
-        for (int sl = q; sl < slots; sl += FN_SPLIT) s += (double)__ldg(p + (size_t)sl * slot_stride);
+        for (; sl + 3 * FN_SPLIT < slots; sl += 4 * FN_SPLIT) {
+          s0 += (double)__ldg(p + (size_t)sl * stride);
+          s1 += (double)__ldg(p + (size_t)(sl + FN_SPLIT) * stride);
+          s2 += (double)__ldg(p + (size_t)(sl + 2 * FN_SPLIT) * stride);
+          s3 += (double)__ldg(p + (size_t)(sl + 3 * FN_SPLIT) * stride);
+        }
+        for (; sl < slots; sl += FN_SPLIT) s0 += (double)__ldg(p + (size_t)sl * stride);
       } else {
         const int nblk = Cpad / 64;
-        const size_t slot_stride = (size_t)nblk * 128 * 320;
+        const size_t stride = (size_t)nblk * 128 * 320;
         const float* p0 = partials + ((size_t)(c / 64) * 128 + 2 * (c % 64)) * 320 + (k & 3) * 80;
         const float* p1 = p0 + 320 + (k + 8) / 4;
         p0 += k / 4;
 #pragma unroll 4
         for (int sl = q; sl < slots; sl += FN_SPLIT)
-          s += (double)__ldg(p0 + (size_t)sl * slot_stride) + (double)__ldg(p1 + (size_t)sl * slot_stride);
+          s0 += (double)__ldg(p0 + (size_t)sl * stride) + (double)__ldg(p1 + (size_t)sl * stride);
       }
-      part[q * K + k] = s;
+      part[q * K + k] = (s0 + s1) + (s2 + s3);
     }
   }
   __syncthreads();
@@ -573,15 +608,7 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
     Gs[k] = s;
     if (grad_filters) grad_filters[(size_t)c * K + k] = (float)s;
   }
-  if (grad_low == nullptr || grad_band == nullptr) return;
-
-  const ChanCoef cc = chan_coef(bank, c);
-  for (int j = tid; j < H; j += FN_THREADS) {
-    const double left = left_tap(cc, (double)bank.n[j]);
-    us[j] = left * (double)bank.window[j];
-    us[K - 1 - j] = left * (double)bank.window[K - 1 - j];
-  }
-  if (tid == 0) us[H] = 2.0 * (cc.f_hi - cc.f_lo) * (double)bank.window[H];
+  if (!want_params) return;
   __syncthreads();
 
   double sabs = 0.0, dot = 0.0;
@@ -596,11 +623,9 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
   auto P = [&](int k) { return (Gs[k] / S - sgn(us[k]) * dot / (S * S)) * (double)bank.window[k]; };
   double dhi = 0.0, dlo = 0.0;
   for (int j = tid; j < H; j += FN_THREADS) {
-    const double nj = (double)bank.n[j];
     const double pl = P(j) + P(K - 1 - j);
-    const double d = nj * 0.5 + 1e-8;
-    dhi += pl * nj * cos(cc.f_hi * nj) / d;
-    dlo -= pl * nj * cos(cc.f_lo * nj) / d;
+    dhi += pl * chi[j];
+    dlo -= pl * clo[j];
   }
   dhi = block_sum(dhi, scratch);
   dlo = block_sum(dlo, scratch);
@@ -770,7 +795,7 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
 
 cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad, int layout,
                             float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st) {
-  const size_t smem = (size_t)((2 + FN_SPLIT) * bank.K + 32) * sizeof(double);
+  const size_t smem = (size_t)((4 + FN_SPLIT) * bank.K + 32) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e =
         ensure_dynamic_smem(reinterpret_cast<const void*>(finalize_kernel), (int)smem);

@@ -110,6 +110,6 @@ bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dty
 size_t tc16_bwd_filter_partial_bytes(int C);
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st, uint8_t* filter_table, long long* phase);
+                                   cudaStream_t st, uint8_t* filter_table, long long* phase, int reserved_sms);
 
 }  // namespace sinc

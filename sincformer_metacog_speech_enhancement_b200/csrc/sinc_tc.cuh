@@ -205,8 +205,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // The diagnostics library (-DSINC_DIAG_SOFT_TIMEOUT) keeps the non-trapping variant: its probes report a timeout
 // through their own status word.  Callers keep the `ok = ok && mbar_wait(..)` form; in the product `ok` stays true.
 constexpr unsigned long long kWaitLimitNs =
-#ifdef SINC_DIAG_SOFT_TIMEOUT
+#if defined(SINC_DIAG_SOFT_TIMEOUT)
     1000000000ull;
+#elif defined(SINC_ABLATION)
+    3000000000ull;    // experiment builds: fail fast
 #else
     30000000000ull;
 #endif

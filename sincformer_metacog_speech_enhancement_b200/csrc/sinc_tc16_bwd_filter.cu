@@ -41,19 +41,15 @@ constexpr int F2_THREADS = 512;  // warps 0-7 grad_y converters (2 groups), 8-9 
 constexpr int F2_N = 32;                    // MMA N (tap columns per shift rho)
 constexpr int F2_TILE = 512;                // samples per tile = 32 K-steps of 16 samples
 constexpr int F2_XLEN = 832;                // bf16 elements per shifted waveform copy: >= 8*31 + 16*36
-constexpr int F2_KPS = 8;                   // K-steps per A ring slot = one grad_y staging stage: ONE producer/issuer handshake
-                                            // (an mbarrier phase check costs ~160 cycles even when complete) per 48 MMAs
-constexpr int F2_RING = 2;                  // TMEM A ring depth (slots of F2_KPS K-steps = 16*F2_KPS columns)
-static_assert(F2_KPS == 8 && (F2_RING & (F2_RING - 1)) == 0 && F2_RING * F2_KPS * 16 <= 256, "A ring geometry");
+constexpr int F2_KPS = 4;                   // K-steps per A ring slot (one producer/issuer handshake per slot)
+constexpr int F2_RING = 4;                  // TMEM A ring depth (slots of F2_KPS K-steps = 16*F2_KPS columns)
+static_assert(8 % F2_KPS == 0 && (F2_RING & (F2_RING - 1)) == 0 && F2_RING * F2_KPS * 16 <= 256, "A ring geometry");
 constexpr int F2_FLUSH = 8;                 // tiles per accumulation window (4096 samples)
 constexpr int F2_DCOLS = 4 * F2_N;          // 128
-constexpr int F2_GSAMP = 256;               // samples per grad_y staging stage (16 K-steps = two ring slots, one per converter
-                                            // group).  One bulk copy moves 1 KB of a row: the single thread that issues the
-                                            // copies was the slowest role of the kernel with 512-byte copies (ncu r02c: it never
-                                            // waited for a free stage while the converters polled g_full ten times per stage)
+constexpr int F2_GSAMP = 128;               // samples per grad_y staging stage (8 K-steps)
 constexpr int F2_GPITCH = F2_GSAMP * 4 + 32;  // bytes per staged row: 32 mod 128, so the row-per-lane LDS.128 of a
                                               // quarter-warp (4 filters x 2 interleaves) hit 8 distinct bank groups
-constexpr int F2_GSTAGES = 2;               // staging ring depth: 128 KB of grad_y in flight per SM
+constexpr int F2_GSTAGES = 4;               // staging ring depth: 128 KB of grad_y in flight per SM
 constexpr int F2_GSTAGE_BYTES = 64 * F2_GPITCH;
 constexpr int F2_SM_G = 0;                  // [F2_GSTAGES][64 rows][F2_GPITCH]
 constexpr int F2_SM_X = F2_SM_G + F2_GSTAGES * F2_GSTAGE_BYTES;  // [buf 2][rho 4][hi/mid 2][F2_XLEN] bf16
@@ -96,8 +92,9 @@ struct BwdFilterTc16Args {
   Bank bank;         // only read when tab != nullptr
   uint8_t* tab;      // filter table for the grad-input kernel (sinc_synth.cuh), or nullptr
 #ifdef SINC_ABLATION
-  int ablate;        // ablation build only: bit 0 converters skip staging reads + conversion + TMEM stores, 1 no MMAs,
-                     // 2 waveform producer skips its work
+  int ablate;        // experiment build only (tools/gf_overlap_repro.py): bit 3 = the issuers do NOT wait for the previous
+                     // window's flush (the overlap under investigation), bit 4 = the flush warps release the accumulator
+                     // set only after their global-memory read-modify-write has completed (membar)
 #endif
 };
 #ifdef SINC_ABLATION
@@ -205,67 +202,40 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     const uint8_t* gbytes = reinterpret_cast<const uint8_t*>(a.g);
     int64_t cc0 = 0;      // ring slots (chunks of F2_KPS K-steps) before the current tile
     int64_t gs = 0;       // staging stages consumed so far
-    // One ring slot = the 8 K-steps (128 samples) of one staging stage, converted in two passes of 4 K-steps so that the
-    // conversion state stays within the register budget (16 staged vectors -> 32 + 32 packed words per pass).  The slot
-    // is waited for once (before the first tcgen05.st of pass 0 -- pass 0 is fetched and converted BEFORE the wait, so
-    // the ~160-cycle phase check and the MMAs still reading the slot overlap the conversion) and handed over once.
-    auto emit_pass = [&](const gvec (&v)[16], int64_t cc, int pass) {
+    auto emit = [&](const gvec (&v)[4 * F2_KPS], int64_t cc) {  // F2_KPS K-steps of this row -> one TMEM ring slot
       const int s = (int)(cc & (F2_RING - 1));
       const uint32_t par = (uint32_t)((cc / F2_RING) & 1);
-      uint32_t hi[32], mid[32];
-      if (GABL(0)) {
+      uint32_t hi[8 * F2_KPS], mid[8 * F2_KPS];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) hi[j] = mid[j] = 0u;
-      } else
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
+      for (int j = 0; j < 4 * F2_KPS; ++j) {
         if constexpr (GB) {  // bf16 pairs are already packed in memory order (even sample in the low half)
           hi[2 * j] = v[j].x;
           hi[2 * j + 1] = v[j].y;
           mid[2 * j] = mid[2 * j + 1] = 0u;
         } else {
-          // the second piece is stored NEGATED (4 instead of 6 instructions per pair); its MMA negates A back
+          // the second piece is stored NEGATED (sinc_tc.cuh: 4 instead of 6 instructions per pair); its MMA negates A back
           tc::split_bf16x2_negmid(v[j].x, v[j].y, hi[2 * j], mid[2 * j]);
           tc::split_bf16x2_negmid(v[j].z, v[j].w, hi[2 * j + 1], mid[2 * j + 1]);
         }
       }
-      if (pass == 0) {
-        ok = ok && tc::mbar_wait(&a_empty[s], par ^ 1);
-        tc::fence_after_sync();
-      }
-      const uint32_t dst = tmem + lane_base + 2 * F2_DCOLS + 16 * F2_KPS * s + 64 * pass;
-      if (GABL(0)) {
-      } else if constexpr (GB) {
+      ok = ok && tc::mbar_wait(&a_empty[s], par ^ 1);
+      tc::fence_after_sync();
+      const uint32_t dst = tmem + lane_base + 2 * F2_DCOLS + 16 * F2_KPS * s;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {  // bf16 grad_y: 8 columns per K-step, no mid piece
-          uint32_t th[8];
+      for (int kk = 0; kk < F2_KPS; ++kk) {  // per K-step: 8 columns hi, 8 columns mid
+        uint32_t th[8], tm8[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) th[e] = hi[8 * kk + e];
-          tc::tmem_st8(dst + 16 * kk, th);
+        for (int e = 0; e < 8; ++e) {
+          th[e] = hi[8 * kk + e];
+          tm8[e] = mid[8 * kk + e];
         }
-      } else {
-        // per K-step 8 columns hi then 8 columns mid: the 4 K-steps of a pass are 64 consecutive columns -- two 32-column
-        // stores instead of eight 8-column ones (every tcgen05.st / LDS / MMA goes through the SM's MIO queue, and the
-        // MMA issuers were stalling on it: ncu r02c, `mio` on the UTCHMMA instructions)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t t32[32];
-#pragma unroll
-          for (int kk = 0; kk < 2; ++kk)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              t32[16 * kk + e] = hi[8 * (2 * half + kk) + e];
-              t32[16 * kk + 8 + e] = mid[8 * (2 * half + kk) + e];
-            }
-          tc::tmem_st32(dst + 32 * half, t32);
-        }
+        tc::tmem_st8(dst + 16 * kk, th);
+        if constexpr (!GB) tc::tmem_st8(dst + 16 * kk + 8, tm8);
       }
-      if (pass == 1) {
-        tc::tmem_st_wait();
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&a_full[s]);
-      }
+      tc::tmem_st_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&a_full[s]);
     };
     for (int64_t it = 0; it < my_tiles; ++it) {
       const int64_t tile = tile_begin + it;
@@ -286,42 +256,37 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         ok = ok && tc::mbar_wait(&g_full[gb], (uint32_t)((gs / F2_GSTAGES) & 1));
         const uint8_t* rowp = gst + gb * F2_GSTAGE_BYTES + cl * GPITCH;
         const int64_t ts = tb + (int64_t)F2_GSAMP * st;
-        {
-          // group g converts the g-th half of the stage (8 K-steps = 128 samples = one ring slot)
-          const int ch = 2 * st + grp;             // slot of the tile
+#pragma unroll
+        for (int u = 0; u < 8 / F2_KPS / 2; ++u) {
+          const int pch = grp + 2 * u;                 // chunk of the stage; chunk ch of the tile belongs to group ch & 1
+          const int ch = (8 / F2_KPS) * st + pch;
           if (F2_KPS * ch < nq) {
+            gvec v[4 * F2_KPS];
             // Interior stage of a full filter block (the common case): no per-element range checks -- the 64-bit
             // compares and selects of the general path were a third of the converters' instructions (ncu r04c),
             // and the converters are co-critical with the MMAs.  (t < 0 never needs a check: the halo is zero at
             // the start of an utterance.)
             const bool interior = all_rows && ts + F2_GSAMP <= T;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-              gvec v[16];
-              const int first = 128 * grp + 64 * pass - 4 * h;   // sample offset of this pass within the stage
-              auto fetch = [&](int i) -> gvec {   // i = 4-sample group within the pass
-                if (first + 4 * i < 0) return halo;              // only (group 0, pass 0, i = 0, h = 1)
-                return *reinterpret_cast<const gvec*>(rowp + G::esz * (first + 4 * i));
-              };
-              if (GABL(0)) {
+            auto fetch = [&](int i) -> gvec {
+              const int off = 16 * F2_KPS * pch - 4 * h + 4 * i;  // sample offset within the stage (-4 only for pch = 0, h = 1)
+              if (pch == 0 && i == 0) return h ? halo : *reinterpret_cast<const gvec*>(rowp);
+              return *reinterpret_cast<const gvec*>(rowp + G::esz * off);
+            };
+            if (interior) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = zero4;
-              } else if (interior) {
+              for (int i = 0; i < 4 * F2_KPS; ++i) v[i] = fetch(i);
+            } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fetch(i);
-              } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  const int64_t tj = ts + (first + 4 * i);
-                  const gvec w = fetch(i);
-                  v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
-                }
+              for (int i = 0; i < 4 * F2_KPS; ++i) {
+                const int64_t tj = ts + (16 * F2_KPS * pch - 4 * h + 4 * i);
+                const gvec w = fetch(i);
+                v[i] = (row_valid && tj >= 0 && tj < T) ? w : zero4;
               }
-              emit_pass(v, cc0 + ch, pass);
             }
+            emit(v, cc0 + ch);
           }
         }
-        if (h) {  // carry the last 4 samples of the row into the next stage (only group 0 uses them)
+        if (h) {  // carry the last 4 samples of the row into the next stage
           const gvec w = *reinterpret_cast<const gvec*>(rowp + G::esz * (F2_GSAMP - 4));
           halo = (row_valid && ts + F2_GSAMP - 4 < T) ? w : zero4;
         }
@@ -329,15 +294,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         if (lane == 0) tc::mbar_arrive(&g_empty[gb]);
         ++gs;
       }
-      if (nq > 16 * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          gvec v[16];
+      if (nq > 8 * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
+        gvec v[4 * F2_KPS];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = zero4;
-          if (pass == 0 && h) v[0] = halo;
-          emit_pass(v, cc0 + 2 * nstg, pass);
-        }
+        for (int i = 0; i < 4 * F2_KPS; ++i) v[i] = zero4;
+        if (h) v[0] = halo;
+        emit(v, cc0 + (8 / F2_KPS) * nstg);
       }
       cc0 += (nq + F2_KPS - 1) / F2_KPS;
     }
@@ -378,12 +340,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           // (tools/gf_debug.py, r02k: 3e-3 on a few filters with > 8 tiles per CTA; never without the overlap).
           // The root cause is not understood yet, so the issuer stalls for the ~3 us a flush takes (once per
           // F2_FLUSH tiles, ~3 % of the kernel) -- the two sets still let the flush overlap the converters.
-          if (win >= 1) ok = ok && tc::mbar_wait(&d_empty[dbuf ^ 1], (uint32_t)(((win - 1) >> 1) & 1));
+          if (win >= 1 && !GABL(3)) ok = ok && tc::mbar_wait(&d_empty[dbuf ^ 1], (uint32_t)(((win - 1) >> 1) & 1));
           acc = 0;
         }
         const uint32_t d0 = tm + F2_DCOLS * dbuf + F2_N * (2 * w);
         uint32_t b0 = xs0 + xb * (8 * F2_XLEN * 2) + (2 * (2 * w)) * F2_XLEN * 2;  // rho = 2w: hi copy, mid copy follows
-        const int nch = (nq + F2_KPS - 1) / F2_KPS;
+        const int nch = (nq + F2_KPS - 1) / F2_KPS;  // K-steps past nq carry zeros in A: harmless
         for (int ch = 0; ch < nch; ++ch) {
           const int s = cc & (F2_RING - 1);
           ok = ok && tc::mbar_wait(&a_full[s], (uint32_t)((cc / F2_RING) & 1));
@@ -392,7 +354,6 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           if (tc::elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < F2_KPS; ++kk) {
-              if (F2_KPS * ch + kk >= nq || GABL(1)) break;   // the last slot of an utterance's final tile is not full (warp-uniform)
               const uint32_t ah = tm + 2 * F2_DCOLS + 16 * F2_KPS * s + 16 * kk, am = ah + 8;
               // consecutive MMAs into the same accumulator serialise on its TMEM read-modify-write: alternate the
               // two shifts this issuer owns so that dependent instructions are never adjacent
@@ -584,7 +545,7 @@ size_t tc16_bwd_filter_partial_bytes(int C) {
 
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st, uint8_t* filter_table, long long* phase) {
+                                   cudaStream_t st, uint8_t* filter_table, long long* phase, int reserved_sms) {
   BwdFilterTc16Args a;
   a.x = x;
   a.xsb = x_stride_b;
@@ -603,7 +564,7 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
 #ifdef SINC_ABLATION
   a.ablate = getenv("SINC_ABLATE_GF") ? atoi(getenv("SINC_ABLATE_GF")) : 0;
 #endif
-  int64_t per_blk = di.sm_count / a.nblk;
+  int64_t per_blk = (di.sm_count - reserved_sms) / a.nblk;   // reserved_sms: SMs left to a kernel running next to this one
   if (per_blk < 1) per_blk = 1;
   if (per_blk > a.ntiles) per_blk = a.ntiles;
   if (per_blk > kMaxPartialSlots) per_blk = kMaxPartialSlots;

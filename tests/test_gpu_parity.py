@@ -298,7 +298,7 @@ def test_abi_error_codes_on_device():
     bad = _lib.Options()
     bad.engine = 7
     assert lib.sinc_forward(ctypes.byref(fb), P(x), 16, P(y), 0, 1, 16, None, 0, None, ctypes.byref(bad)) == -8   # engine
-    bad.engine, bad.reserved_sms = 0, 65
+    bad.engine, bad.reserved_sms = 0, 129
     assert lib.sinc_forward(ctypes.byref(fb), P(x), 16, P(y), 0, 1, 16, None, 0, None, ctypes.byref(bad)) == -2   # reserved SMs
     used = ctypes.c_int32(-1)
     opt = _lib.Options()

@@ -11,8 +11,7 @@ PLANS = {
                               15: "barriers only"}),
     "bi": ("SINC_ABLATE_BI", {0: "full", 3: "epilogue idle", 12: "producers idle (TMA boxes still arrive)", 15: "MMA issue only",
                               16: "no MMAs", 31: "barriers + TMA boxes only"}),
-    "gf": ("SINC_ABLATE_GF", {0: "full", 1: "converters idle (bulk copies still arrive)", 2: "no MMAs", 3: "copies + barriers only",
-                              4: "waveform producer idle"}),
+    "gf": ("SINC_ABLATE_GF", {0: "full", 8: "no wait for the previous window's flush (results may be wrong)"}),
 }
 
 if len(sys.argv) > 2 and sys.argv[1] == "child":
