@@ -51,6 +51,12 @@ int sinc_tc_mma_rate(int N, int nacc, int count, int a_from_tmem, long long* cyc
  * 4*j + 2*u + e of a half holds lane (t / 4) + 8 * u, column 8 * j + 2 * (t % 4) + e. */
 int sinc_tc_ld16x256_probe(uint32_t* out2048, void* stream);
 
+/* Diagnostic: the rate at which 148 persistent CTAs can stream a (B,64,T) fp32 activation from HBM into shared memory
+ * with no consumer at all -- the ceiling of the operand feed of the backward kernels.  mode 0/1/2: 1-D bulk copies of
+ * 512 B / 1 KB / 2 KB row pieces (64 rows per stage), `depth` stages in flight per SM; mode 3: plain LDG.128.
+ * T % 512 == 0, C == 64.  Time it with events around the call (tools/feed_probe.py). */
+int sinc_feed_probe(const float* g, int64_t B, int32_t C, int64_t T, int mode, int depth, float* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

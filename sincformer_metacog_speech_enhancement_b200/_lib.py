@@ -26,7 +26,7 @@ ABI_SYMBOLS = (
     "sinc_gn_gelu_backward",
 )
 # every symbol include/sinc_b200_diag.h declares (libsinc_b200_diag.so: tests and tools only)
-DIAG_SYMBOLS = ("sinc_tc_probe", "sinc_tc_mma_rate", "sinc_mbar_wait_cost", "sinc_tc_ld16x256_probe")
+DIAG_SYMBOLS = ("sinc_tc_probe", "sinc_tc_mma_rate", "sinc_mbar_wait_cost", "sinc_tc_ld16x256_probe", "sinc_feed_probe")
 
 
 class FilterBank(ctypes.Structure):
@@ -119,6 +119,8 @@ def _declare_diag(lib):
                                   c.c_void_p]
     lib.sinc_tc_ld16x256_probe.restype = c.c_int
     lib.sinc_tc_ld16x256_probe.argtypes = [c.c_void_p, c.c_void_p]
+    lib.sinc_feed_probe.restype = c.c_int
+    lib.sinc_feed_probe.argtypes = [c.c_void_p, c.c_int64, c.c_int32, c.c_int64, c.c_int, c.c_int, c.c_void_p, c.c_void_p]
 
 
 def library_path() -> str:

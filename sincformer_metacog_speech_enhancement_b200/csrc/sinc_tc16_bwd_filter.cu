@@ -44,12 +44,17 @@ constexpr int F2_XLEN = 832;                // bf16 elements per shifted wavefor
 constexpr int F2_KPS = 4;                   // K-steps per A ring slot (one producer/issuer handshake per slot)
 constexpr int F2_RING = 4;                  // TMEM A ring depth (slots of F2_KPS K-steps = 16*F2_KPS columns)
 static_assert(8 % F2_KPS == 0 && (F2_RING & (F2_RING - 1)) == 0 && F2_RING * F2_KPS * 16 <= 256, "A ring geometry");
+// chunks (ring slots) per staging stage: must be even -- chunk ch of a tile belongs to converter group ch & 1
 constexpr int F2_FLUSH = 8;                 // tiles per accumulation window (4096 samples)
 constexpr int F2_DCOLS = 4 * F2_N;          // 128
-constexpr int F2_GSAMP = 128;               // samples per grad_y staging stage (8 K-steps)
+constexpr int F2_GSAMP = 256;               // samples per grad_y staging stage (16 K-steps = four ring slots): one bulk copy moves
+                                            // 1 KB of a row.  With 512-byte copies the single issuing thread caps the feed at
+                                            // 5.2 TB/s chip-wide whatever the depth (one UBLKCP per ~24 cycles); 1 KB copies with
+                                            // 128 KB in flight stream at 6.5 TB/s (tools/feed_probe.py, profiles/r02_feed_probe.log)
+constexpr int F2_SPS = F2_GSAMP / 16;       // K-steps per staging stage
 constexpr int F2_GPITCH = F2_GSAMP * 4 + 32;  // bytes per staged row: 32 mod 128, so the row-per-lane LDS.128 of a
                                               // quarter-warp (4 filters x 2 interleaves) hit 8 distinct bank groups
-constexpr int F2_GSTAGES = 4;               // staging ring depth: 128 KB of grad_y in flight per SM
+constexpr int F2_GSTAGES = 2;               // staging ring depth: 128 KB of grad_y in flight per SM
 constexpr int F2_GSTAGE_BYTES = 64 * F2_GPITCH;
 constexpr int F2_SM_G = 0;                  // [F2_GSTAGES][64 rows][F2_GPITCH]
 constexpr int F2_SM_X = F2_SM_G + F2_GSTAGES * F2_GSTAGE_BYTES;  // [buf 2][rho 4][hi/mid 2][F2_XLEN] bf16
@@ -256,10 +261,10 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         ok = ok && tc::mbar_wait(&g_full[gb], (uint32_t)((gs / F2_GSTAGES) & 1));
         const uint8_t* rowp = gst + gb * F2_GSTAGE_BYTES + cl * GPITCH;
         const int64_t ts = tb + (int64_t)F2_GSAMP * st;
-#pragma unroll
-        for (int u = 0; u < 8 / F2_KPS / 2; ++u) {
+#pragma unroll 1
+        for (int u = 0; u < F2_SPS / F2_KPS / 2; ++u) {
           const int pch = grp + 2 * u;                 // chunk of the stage; chunk ch of the tile belongs to group ch & 1
-          const int ch = (8 / F2_KPS) * st + pch;
+          const int ch = (F2_SPS / F2_KPS) * st + pch;
           if (F2_KPS * ch < nq) {
             gvec v[4 * F2_KPS];
             // Interior stage of a full filter block (the common case): no per-element range checks -- the 64-bit
@@ -294,12 +299,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         if (lane == 0) tc::mbar_arrive(&g_empty[gb]);
         ++gs;
       }
-      if (nq > 8 * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
+      if (nq > F2_SPS * nstg && grp == 0) {  // the K-step after the last stage: only the carried samples are non-zero
         gvec v[4 * F2_KPS];
 #pragma unroll
         for (int i = 0; i < 4 * F2_KPS; ++i) v[i] = zero4;
         if (h) v[0] = halo;
-        emit(v, cc0 + (8 / F2_KPS) * nstg);
+        emit(v, cc0 + (F2_SPS / F2_KPS) * nstg);
       }
       cc0 += (nq + F2_KPS - 1) / F2_KPS;
     }
