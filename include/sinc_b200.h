@@ -102,7 +102,11 @@ typedef struct sinc_options {
   long long* phase_stamps;
 } sinc_options;
 
-/* Bytes of device scratch sinc_forward / sinc_backward need for this shape (never 0). */
+/* Bytes of device scratch sinc_forward / sinc_backward need for this shape (never 0).  For lengths that are not a
+ * multiple of 8 samples this includes room for a zero-padded copy of grad_y with 16-byte aligned rows: the 16-bit
+ * tensor-core backward kernels stage grad_y with bulk copies / TMA boxes, so sinc_backward re-pitches a ragged grad_y
+ * once (one extra streaming pass, exact) instead of dropping to a slower kernel family.  A smaller workspace (at least
+ * the size for an aligned length) is still accepted: the backward then uses the kernels that take any length. */
 size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K);
 
 /* Filter synthesis alone: parameters -> (C,K) fp32 filter bank, row-major.

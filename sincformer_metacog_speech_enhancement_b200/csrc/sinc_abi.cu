@@ -42,6 +42,17 @@ WorkspaceLayout workspace_layout(int C, int K) {
   return wl;
 }
 
+RepitchLayout repitch_layout(int64_t B, int64_t T, int C, int K) {
+  const WorkspaceLayout wl = workspace_layout(C, K);
+  RepitchLayout rl;
+  rl.Tp = (T + 7) / 8 * 8;
+  rl.g_offset = (wl.total_bytes + 255) / 256 * 256;
+  rl.x_offset = rl.g_offset + ((size_t)B * C * rl.Tp * 4 + 255) / 256 * 256;
+  rl.gx_offset = rl.x_offset + ((size_t)B * rl.Tp * 4 + 255) / 256 * 256;
+  rl.total_bytes = rl.gx_offset + ((size_t)B * rl.Tp * 4 + 255) / 256 * 256 + 256;
+  return rl;
+}
+
 static int check_bank(const sinc_filterbank* fb) {
   if (!fb || !fb->low_hz || !fb->band_hz || !fb->window) return SINC_E_NULL;
   if (fb->C < 1 || fb->K < 1 || (fb->K % 2) == 0) return SINC_E_SHAPE;
@@ -84,10 +95,12 @@ const char* sinc_strerror(int code) {
 uint64_t sinc_kernel_launch_count(void) { return launch_count(); }
 
 size_t sinc_workspace_bytes(int64_t B, int64_t T, int32_t C, int32_t K) {
-  (void)B;
-  (void)T;
   if (C < 1) C = 1;
   if (K < 1) K = 1;
+  if (B < 1) B = 1;
+  if (T < 1) T = 1;
+  // lengths that are not a multiple of 8 samples: room for the re-pitched copies the backward makes (sinc_internal.h)
+  if (T % 8 != 0) return repitch_layout(B, T, C, K).total_bytes;
   return workspace_layout(C, K).total_bytes;
 }
 
@@ -184,6 +197,39 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
   const Bank bank = to_bank(fb);
   if (!fma_supported(bank.C, bank.K, di)) return SINC_E_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
+  // Ragged rows: re-pitch grad_y (and x) into the workspace tail and run the tensor-core kernels on the padded copy.
+  // Only when the engine may use them, the 16-bit kernels take the shape otherwise, and the caller sized the workspace
+  // with sinc_workspace_bytes(B, T, ..) for this T.
+  float* grad_x_final = nullptr;
+  int64_t T_final = T;
+  {
+    const int esz = gy_dtype == SINC_DTYPE_F32 ? 4 : 2;
+    const bool rows_aligned = T % (16 / esz) == 0 && reinterpret_cast<uintptr_t>(grad_y) % 16 == 0;
+    const bool tc_wanted = o.engine == SINC_ENGINE_AUTO || o.engine == SINC_ENGINE_TC;
+    if (!rows_aligned && tc_wanted && bank.K <= 256 && (grad_x == nullptr || bank.C <= 64) && T % 8 != 0) {
+      const RepitchLayout rl = repitch_layout(B, T, bank.C, bank.K);
+      if (workspace && workspace_bytes >= rl.total_bytes) {
+        uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);
+        void* g4 = base + rl.g_offset;
+        float* x4 = reinterpret_cast<float*>(base + rl.x_offset);
+        float* gx4 = reinterpret_cast<float*>(base + rl.gx_offset);
+        cudaError_t e2 = launch_pad_rows(grad_y, T, g4, rl.Tp, B * bank.C, T, esz, st);
+        if (e2 != cudaSuccess) return (int)e2;
+        if (want_params) {
+          e2 = launch_pad_rows(x, x_stride_b, x4, rl.Tp, B, T, 4, st);
+          if (e2 != cudaSuccess) return (int)e2;
+          x = x4;
+          x_stride_b = rl.Tp;
+        }
+        grad_y = g4;
+        if (grad_x) {
+          grad_x_final = grad_x;
+          grad_x = gx4;
+        }
+        T = rl.Tp;
+      }
+    }
+  }
   cudaError_t e;
   int mask = 0;
   const int engine = o.engine;
@@ -237,6 +283,10 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     if (e != cudaSuccess) return (int)e;
     mask |= (use_tc || use_tc16) ? 2 : 0;
     mask |= use_tc16 ? 16 : 0;
+  }
+  if (grad_x_final) {  // the padded grad-input rows back to the caller's (B,T) tensor
+    e = launch_pad_rows(grad_x, T, grad_x_final, T_final, B, T_final, 4, st);
+    if (e != cudaSuccess) return (int)e;
   }
   if (o.engines_used) *o.engines_used = mask;
   return 0;

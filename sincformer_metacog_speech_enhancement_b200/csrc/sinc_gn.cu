@@ -265,6 +265,38 @@ gn_param_grad_kernel(const float2* __restrict__ partial, int64_t B, int C, int c
   }
 }
 
+// ---- row re-pitch (sinc_backward for ragged lengths, sinc_internal.h): dst[r][0..dpitch) = src[r][0..n), zero beyond n ----
+template <typename E>
+__global__ void __launch_bounds__(256) pad_rows_kernel(const E* __restrict__ src, int64_t spitch, E* __restrict__ dst,
+                                                       int64_t dpitch, int64_t n) {
+  const int64_t row = blockIdx.y;
+  const E* s = src + row * spitch;
+  E* d = dst + row * dpitch;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < dpitch; i += (int64_t)gridDim.x * 256)
+    d[i] = i < n ? __ldg(s + i) : E(0);
+}
+
+cudaError_t launch_pad_rows(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t rows, int64_t n,
+                            int esz, cudaStream_t st) {
+  if (rows > 65535LL * 32768) return cudaErrorInvalidValue;
+  int64_t gx = (dst_pitch + 256 * 8 - 1) / (256 * 8);   // ~8 elements per thread
+  if (gx < 1) gx = 1;
+  if (gx > 1024) gx = 1024;
+  // gridDim.y is limited to 65535: fold larger row counts into several launches
+  for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+    const int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+    dim3 grid((unsigned)gx, (unsigned)nr);
+    if (esz == 4)
+      pad_rows_kernel<uint32_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint32_t*>(src) + r0 * src_pitch, src_pitch,
+                                                      reinterpret_cast<uint32_t*>(dst) + r0 * dst_pitch, dst_pitch, n);
+    else
+      pad_rows_kernel<uint16_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src) + r0 * src_pitch, src_pitch,
+                                                      reinterpret_cast<uint16_t*>(dst) + r0 * dst_pitch, dst_pitch, n);
+    count_launch();
+  }
+  return cudaGetLastError();
+}
+
 static int gn_check(int64_t B, int64_t T, int C, int G, const void* a, const void* b2) {
   if (B < 1 || T < 1 || C < 1 || G < 1 || C % G) return SINC_E_SHAPE;
   if (reinterpret_cast<uintptr_t>(a) % 4 || reinterpret_cast<uintptr_t>(b2) % 4) return SINC_E_ALIGN;

@@ -68,6 +68,22 @@ struct WorkspaceLayout {
 };
 WorkspaceLayout workspace_layout(int C, int K);
 
+// Ragged lengths (T % 4 != 0 for fp32 / T % 8 != 0 for bf16 grad_y, or a grad_y pointer that is not 16-byte aligned): the
+// tensor-core backward kernels stage grad_y with bulk copies and TMA boxes, which need every row to start on a 16-byte
+// boundary.  sinc_backward then re-pitches grad_y (and the waveform) once into the tail of the workspace with rows of
+// Tp = T rounded up to 8 samples, zero filled -- exact, because the convolution pads with zeros anyway -- and runs the
+// same kernels on the padded copy: one extra streaming pass over grad_y instead of a 5x slower kernel family.
+struct RepitchLayout {
+  int64_t Tp;            // padded row length
+  size_t g_offset;       // (B,C,Tp) in grad_y's element type (sized for fp32)
+  size_t x_offset;       // (B,Tp) fp32
+  size_t gx_offset;      // (B,Tp) fp32
+  size_t total_bytes;    // workspace size including the padded copies
+};
+RepitchLayout repitch_layout(int64_t B, int64_t T, int C, int K);
+cudaError_t launch_pad_rows(const void* src, int64_t src_pitch, void* dst, int64_t dst_pitch, int64_t rows, int64_t n,
+                            int esz, cudaStream_t st);   // dst[r][0..dst_pitch) = src[r][0..n), zeros beyond n
+
 // ---- FP32-FMA engine (sinc_fma.cu) ---------------------------------------------------------------
 bool fma_supported(int C, int K, const DeviceInfo& di);
 cudaError_t launch_synthesize(const Bank& bank, float* filters_out, cudaStream_t st);

@@ -96,7 +96,8 @@ struct BwdInputTc16Args {
 #ifdef SINC_ABLATION
   int ablate;              // ablation build only (tools/ablate.py): bit 0 epilogue skips col2im, 1 epilogue skips the TMEM
                            // load too, 2 producers skip conversion + plane stores, 3 producers skip the staging reads too,
-                           // 4 the issuer issues no MMAs (commits only).  Results are garbage by construction.
+                           // 4 the issuer issues no MMAs (commits only), 5 every TMA box reads the same few (L2-resident)
+                           // stages: a "perfect feed".  Results are garbage by construction.
 #endif
 };
 #ifdef SINC_ABLATION
@@ -299,7 +300,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
         if (tc::elect_one()) {
           uint64_t* bar = &my_full[q % H2_NBOX];
           tc::mbar_expect_tx(bar, BOXB);
-          tc::tensor_load_3d(stg0 + (q % H2_NBOX) * H2_STG_BOX, &gmap, (int)(c0 + (int64_t)H2_NS * i + 32 * pw), 0, (int)b, bar);
+          tc::tensor_load_3d(stg0 + (q % H2_NBOX) * H2_STG_BOX, &gmap,
+                             (int)(c0 + (int64_t)H2_NS * (ABL(5) ? (i & 3) : i) + 32 * pw), 0, (int)(ABL(5) ? 0 : b), bar);
         }
         __syncwarp();
       };

@@ -76,6 +76,35 @@ def test_ragged_and_wide_at_realistic_length(C, T):
     16-bit tensor-core kernel for every length."""
     out = full_check(C, 251, 16000, 4, T, seed=C + T)
     assert out["engines"]["fwd"] == "tc16", out["engines"]
+    if C <= 64:      # ragged lengths stay on the 16-bit tensor-core kernels in the backward too (one re-pitch pass of grad_y)
+        assert out["engines"] == ALL_TC16, out["engines"]
+
+
+def test_ragged_length_costs_one_extra_pass_not_a_kernel_family():
+    """T = 48 001 used to drop forward and grad-filter to the FMA engine (7.6x).  Now the step at
+    48 001 must stay within 1.6x of the step at 48 000 (one extra streaming pass over grad_y + plain-store epilogue)."""
+    times = {}
+    for T in (48000, 48001):
+        dut = sb.SincConv1d(64, 251, sample_rate=16000).to(dev())
+        x = torch.randn(32, 1, T, device=dev())
+        g = torch.randn(32, 64, T, device=dev())
+
+        def step():
+            xr = x.detach().requires_grad_(True)
+            dut.low_hz_.grad = dut.band_hz_.grad = None
+            dut(xr).backward(g)
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        times[T] = e0.elapsed_time(e1) / 10
+    print(f"step at T=48000: {times[48000]:.3f} ms, at T=48001: {times[48001]:.3f} ms ({times[48001] / times[48000]:.2f}x)")
+    assert times[48001] <= 1.6 * times[48000], times
 
 
 def test_module_dtype_casts_like_the_reference():

@@ -134,7 +134,9 @@ def test_tc16_forward_ragged_lengths(T, out_dtype):
 TC_BWD_SHAPES = [
     (64, 251, 16000, 2, 1000),
     (64, 251, 16000, 1, 16000),
-    (64, 251, 16000, 7, 4099),      # ragged T: grad-input TC takes any T (forward / grad-filter fall back to FMA)
+    (64, 251, 16000, 7, 4099),      # ragged T: the backward re-pitches grad_y once and runs the 16-bit kernels on the copy
+    (64, 251, 16000, 3, 4102),
+    (16, 65, 8000, 5, 1001),
     (33, 127, 8000, 3, 3000),
     (64, 251, 16000, 3, 4100),
     (64, 251, 8000, 5, 100),
@@ -163,10 +165,13 @@ def test_tc_backward_vs_oracle(engine, C, K, sr, B, T):
     # the forward runs under AUTO (engine "tc" refuses shapes its forward cannot take); the backward under `engine`
     out = run_dut(dut, x, g, bwd_engine=engine)
     eng = out["engines"]
-    if T % 4 == 0 and K <= (256 if engine == "tc" else 312):
+    # ragged lengths: under "tc" the backward re-pitches grad_y once and stays on the 16-bit kernels (needs both passes
+    # to fit: K <= 256, C <= 64 for grad-input); under "tc_tf32" only grad-input takes any length
+    ragged16 = engine == "tc" and T % 4 != 0 and K <= 256 and C <= 64
+    if (T % 4 == 0 or ragged16) and K <= (256 if engine == "tc" else 312):
         assert eng["bwd_filter"] == ("tc16" if engine == "tc" else "tc_tf32"), eng
     if C <= 64 and K <= 256:
-        assert eng["bwd_input"] == ("tc16" if engine == "tc" and T % 4 == 0 else "tc_tf32"), eng
+        assert eng["bwd_input"] == ("tc16" if engine == "tc" and (T % 4 == 0 or ragged16) else "tc_tf32"), eng
     check_against(orc, out, x, g)
 
 

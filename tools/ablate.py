@@ -9,8 +9,9 @@ PLANS = {
     "fw": ("SINC_ABLATE_FW", {0: "full", 1: "epilogue idle (stores of stale staging)", 2: "no stores to y", 3: "epilogue idle + no stores",
                               4: "no MMAs", 8: "producers idle", 12: "no MMAs, producers idle (stores only)",
                               15: "barriers only"}),
-    "bi": ("SINC_ABLATE_BI", {0: "full", 3: "epilogue idle", 12: "producers idle (TMA boxes still arrive)", 15: "MMA issue only",
-                              16: "no MMAs", 31: "barriers + TMA boxes only"}),
+    "bi": ("SINC_ABLATE_BI", {0: "full", 32: "full, boxes from L2 (perfect feed)", 3: "epilogue idle", 12: "producers idle (TMA boxes still arrive)",
+                              15: "MMA issue only", 47: "MMA issue only, boxes from L2", 16: "no MMAs", 31: "barriers + TMA boxes only",
+                              63: "barriers + TMA boxes from L2 only"}),
     "gf": ("SINC_ABLATE_GF", {0: "full", 8: "no wait for the previous window's flush (results may be wrong)"}),
 }
 
