@@ -45,7 +45,16 @@ constexpr int F2_KPS = 4;                   // K-steps per A ring slot (one prod
 constexpr int F2_RING = 4;                  // TMEM A ring depth (slots of F2_KPS K-steps = 16*F2_KPS columns)
 static_assert(8 % F2_KPS == 0 && (F2_RING & (F2_RING - 1)) == 0 && F2_RING * F2_KPS * 16 <= 256, "A ring geometry");
 // chunks (ring slots) per staging stage: must be even -- chunk ch of a tile belongs to converter group ch & 1
-constexpr int F2_FLUSH = 8;                 // tiles per accumulation window (4096 samples)
+#ifndef F2_FLUSH_TILES
+#define F2_FLUSH_TILES 8
+#endif
+constexpr int F2_FLUSH = F2_FLUSH_TILES;    // tiles per accumulation window (4096 samples = 256 K-steps).  The tensor core's fp32
+                                            // accumulation truncates, so a chain of n accumulations is biased by ~n * 2^-24: this
+                                            // is most of the 1.3e-5 error of G (5.7e-6 with 1024-sample windows, where the 16-bit
+                                            // operand split is what is left) and the reason two shardings of one batch differ by
+                                            // ~1.4e-5 in the parameter gradients.  Shorter windows were measured and cost more than
+                                            // they are worth: a flush is ~6 us with the issuers waiting for it, ~2.6 us overlapped
+                                            // (profiles/r02_grad_filter_window_length.log: 2 tiles: +30 % / +13 % of the kernel).
 constexpr int F2_DCOLS = 4 * F2_N;          // 128
 constexpr int F2_GSAMP = 256;               // samples per grad_y staging stage (16 K-steps = four ring slots): one bulk copy moves
                                             // 1 KB of a row.  With 512-byte copies the single issuing thread caps the feed at

@@ -149,7 +149,25 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   float* wsc = stage;  // fp32 filters [16][U_WPITCH], zero outside [0, K)
   for (int i = tid; i < U_FB * U_WPITCH; i += U_THREADS) wsc[i] = 0.f;
   __syncthreads();
-  if (warp < U_FB / 2) {  // warps 0-7: two filters each, synthesised side by side (sinc_synth.cuh) -- one round
+  if (FABL(4)) {   // experiment: the round-1 prologue (one filter per warp call, two rounds on 11 warps)
+    for (int cl = warp; cl < U_FB; cl += U_THREADS / 32) {
+      const int c = c0 + cl;
+      float mx = 0.f;
+      if (c < C)
+        synth_filter_warp(a.bank, c, lane, [&](int k, double w) {
+          const float wf = (float)w;
+          wsc[cl * U_WPITCH + k] = wf;
+          mx = fmaxf(mx, fabsf(wf));
+        });
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const int se = u_scale_exp(mx);
+      if (lane == 0) winv[cl] = u_pow2(-se);
+      const float sw = u_pow2(se);
+      __syncwarp();
+      for (int k = lane; k < K; k += 32) wsc[cl * U_WPITCH + k] *= sw;
+    }
+  } else if (warp < U_FB / 2) {  // warps 0-7: two filters each, synthesised side by side (sinc_synth.cuh) -- one round
     const int cl2[2] = {2 * warp, 2 * warp + 1};
     float mx[2] = {0.f, 0.f};
     const bool va = c0 + cl2[0] < C, vb = c0 + cl2[1] < C;
