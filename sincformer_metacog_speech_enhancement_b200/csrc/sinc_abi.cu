@@ -38,7 +38,8 @@ WorkspaceLayout workspace_layout(int C, int K) {
   const size_t tc16_bytes = tc16_bwd_filter_partial_bytes(C);
   if (tc16_bytes > wl.partial_bytes) wl.partial_bytes = tc16_bytes;
   wl.table_offset = (wl.partial_bytes + 255) / 256 * 256;
-  wl.total_bytes = wl.table_offset + kFilterTableBytes + 256;
+  wl.sync_offset = wl.table_offset + kFilterTableBytes;
+  wl.total_bytes = wl.sync_offset + 256 + 256;
   return wl;
 }
 
@@ -254,16 +255,31 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
                          (engine == SINC_ENGINE_AUTO && kAutoPrefersTcBwdFilter);
     const bool use_tc16 = want_tc && tc16_ok && engine != SINC_ENGINE_TC_TF32;
     const bool use_tc = want_tc && tc_ok && !use_tc16;
-    if (use_tc16)
-      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table, o.phase, o.reserved_sms);
-    else if (use_tc)
+    bool fused = false;
+    if (use_tc16) {
+      // C <= 64: the kernel reduces its partial tiles and applies the chain rule in its own tail (one launch fewer)
+      FusedFinalize fin;
+#ifdef SINC_ABLATION
+      const bool split_finalize = getenv("SINC_SPLIT_FINALIZE") != nullptr;   // A/B against the separate finalize_kernel
+#else
+      const bool split_finalize = false;
+#endif
+      fin.sync_word = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(partials) + wl.sync_offset);
+      fin.grad_low = grad_low;
+      fin.grad_band = grad_band;
+      fin.grad_filters = grad_filters;
+      e = launch_bwd_filter_tc16(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st, filter_table, o.phase,
+                                 o.reserved_sms, (grad_low && grad_band && !split_finalize) ? &fin : nullptr, &fused);
+    } else if (use_tc)
       e = launch_bwd_filter_tc(bank, x, x_stride_b, grad_y, partials, &slots, B, T, di, st);
     else
       e = launch_bwd_filter_fma(bank, x, x_stride_b, grad_y, gy_dtype, partials, &slots, B, T, di, st);
     if (e != cudaSuccess) return (int)e;
-    e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, use_tc16 ? 2 : use_tc ? 1 : 0, grad_low, grad_band,
-                        grad_filters, st);
-    if (e != cudaSuccess) return (int)e;
+    if (!fused) {
+      e = launch_finalize(bank, partials, slots, wl.Cpad, wl.Kpad, use_tc16 ? 2 : use_tc ? 1 : 0, grad_low, grad_band,
+                          grad_filters, st);
+      if (e != cudaSuccess) return (int)e;
+    }
     mask |= (use_tc || use_tc16) ? 4 : 0;
     mask |= use_tc16 ? 32 : 0;
   }

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "sinc_internal.h"
+#include "sinc_finalize.cuh"
 #include "sinc_synth.cuh"
 
 namespace sinc {
@@ -506,20 +507,6 @@ __global__ void __launch_bounds__(BI_THREADS, 1) bwd_input_fma_kernel(const BwdI
 constexpr int FN_THREADS = 1024;
 constexpr int FN_SPLIT = 4;  // slot quarters summed in parallel, combined in fixed order
 
-__device__ __forceinline__ double block_sum(double v, double* scratch) {
-  v = warp_sum(v);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  double s = 0.0;
-#pragma unroll
-  for (int w = 0; w < FN_THREADS / 32; ++w) s += scratch[w];
-  return s;
-}
-
-__device__ __forceinline__ double sgn(double v) { return (double)((v > 0.0) - (v < 0.0)); }
-
 // layout 0: FMA partial tiles [slot][Cpad][Kpad];  layout 1: tcgen05 partial tiles [slot][nblk][128][320] with
 // row (c_local, h) and column rho*80 + n holding tap k = 4n + rho - 8h (sinc_tc_bwd_filter.cu);  layout 2: 16-bit
 // tcgen05 partial tiles [slot][nblk][128][128], row (c_local, h), column rho*32 + n holding the single tap
@@ -529,11 +516,11 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
                                                               float* grad_low, float* grad_band,
                                                               float* grad_filters) {
   extern __shared__ __align__(16) double dsm[];
-  const int K = bank.K, H = (K - 1) / 2;
+  const int K = bank.K;
   double* Gs = dsm;                  // [K] reduced grad-filter
   double* us = dsm + K;              // [K] un-normalised taps u
-  double* scratch = us + K;          // [32]
-  double* part = scratch + 32;       // [FN_SPLIT][K]
+  double* scratch = us + K;          // [64]
+  double* part = scratch + 64;       // [FN_SPLIT][K]
   double* chi = part + FN_SPLIT * K; // [H] n_j cos(f_hi n_j) / d_j   (the chain-rule factors: independent of G)
   double* clo = chi + K;             // [H] n_j cos(f_lo n_j) / d_j
   const int c = blockIdx.x;
@@ -545,18 +532,7 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
   // not depend on the reduced grad-filter -- the un-normalised taps and the cosine factors of the chain rule -- is
   // computed by the LAST warps while the others already have their partial-tile loads in flight, and the loads
   // themselves are issued sixteen at a time (four independent fp64 chains) instead of four.
-  if (want_params && tid >= FN_THREADS - 128) {
-    for (int j = tid - (FN_THREADS - 128); j < H; j += 128) {
-      const double nj = (double)bank.n[j];
-      const double left = left_tap(cc, nj);
-      us[j] = left * (double)bank.window[j];
-      us[K - 1 - j] = left * (double)bank.window[K - 1 - j];
-      const double d = nj * 0.5 + 1e-8;
-      chi[j] = nj * cos(cc.f_hi * nj) / d;
-      clo[j] = nj * cos(cc.f_lo * nj) / d;
-    }
-    if (tid == FN_THREADS - 1) us[H] = 2.0 * (cc.f_hi - cc.f_lo) * (double)bank.window[H];
-  }
+  if (want_params && tid >= FN_THREADS - 128) finalize_factors(bank, cc, tid - (FN_THREADS - 128), 128, us, chi, clo);
   {
     const int q = tid / (FN_THREADS / FN_SPLIT), kk = tid % (FN_THREADS / FN_SPLIT);
     for (int k = kk; k < K; k += FN_THREADS / FN_SPLIT) {
@@ -611,34 +587,7 @@ __global__ void __launch_bounds__(FN_THREADS) finalize_kernel(const Bank bank, c
   if (!want_params) return;
   __syncthreads();
 
-  double sabs = 0.0, dot = 0.0;
-  for (int k = tid; k < K; k += FN_THREADS) {
-    sabs += fabs(us[k]);
-    dot += Gs[k] * us[k];
-  }
-  const double S = block_sum(sabs, scratch) + 1e-8;
-  dot = block_sum(dot, scratch);
-
-  // P_k = dL/du_k * window_k,  dL/du_k = G_k/S - sign(u_k) * dot / S^2
-  auto P = [&](int k) { return (Gs[k] / S - sgn(us[k]) * dot / (S * S)) * (double)bank.window[k]; };
-  double dhi = 0.0, dlo = 0.0;
-  for (int j = tid; j < H; j += FN_THREADS) {
-    const double pl = P(j) + P(K - 1 - j);
-    dhi += pl * chi[j];
-    dlo -= pl * clo[j];
-  }
-  dhi = block_sum(dhi, scratch);
-  dlo = block_sum(dlo, scratch);
-  if (tid == 0) {
-    const double pc = P(H);
-    const double d_fhi = dhi + 2.0 * pc;
-    const double d_flo = dlo - 2.0 * pc;
-    const double d_high = d_fhi / bank.sr;
-    const double d_low_direct = d_flo / bank.sr;
-    const double un = cc.unclamped ? 1.0 : 0.0;
-    grad_band[c] = (float)(un * d_high * sgn((double)bank.band_hz[c]));
-    grad_low[c] = (float)((d_low_direct + un * d_high) * sgn((double)bank.low_hz[c]));
-  }
+  finalize_chain_rule<FN_THREADS>(bank, cc, c, Gs, us, chi, clo, scratch, grad_low, grad_band);
 }
 
 // debug / test: filters alone
@@ -795,7 +744,7 @@ cudaError_t launch_bwd_filter_fma(const Bank& bank, const float* x, int64_t x_st
 
 cudaError_t launch_finalize(const Bank& bank, const float* ws_partials, int slots, int Cpad, int Kpad, int layout,
                             float* grad_low, float* grad_band, float* grad_filters, cudaStream_t st) {
-  const size_t smem = (size_t)((4 + FN_SPLIT) * bank.K + 32) * sizeof(double);
+  const size_t smem = (size_t)((4 + FN_SPLIT) * bank.K + 64) * sizeof(double);
   if (smem > 48 * 1024) {
     cudaError_t e =
         ensure_dynamic_smem(reinterpret_cast<const void*>(finalize_kernel), (int)smem);

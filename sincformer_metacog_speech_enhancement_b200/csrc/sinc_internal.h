@@ -64,6 +64,7 @@ struct WorkspaceLayout {
   int Kpad;         // K rounded up to kTapBlock
   size_t partial_bytes;
   size_t table_offset;  // filter table (sinc_synth.cuh), from the 256-byte aligned workspace base
+  size_t sync_offset;   // 256 bytes after the table: the arrival word of the fused finalize (sinc_tc16_bwd_filter.cu)
   size_t total_bytes;
 };
 WorkspaceLayout workspace_layout(int C, int K);
@@ -124,8 +125,17 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
 int64_t tc16_fwd_tiles_per_row(int64_t T);
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di);
 size_t tc16_bwd_filter_partial_bytes(int C);
+// `fin` non-null and C <= 64: the kernel finalises itself (fixed-order fp64 reduction of the partial tiles + chain rule in
+// its tail) and the caller must NOT launch finalize_kernel; *fused_out says which happened.
+struct FusedFinalize {
+  unsigned long long* sync_word;  // 8-byte aligned word in the workspace (any contents)
+  float* grad_low;
+  float* grad_band;
+  float* grad_filters;            // may be null
+};
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st, uint8_t* filter_table, long long* phase, int reserved_sms);
+                                   cudaStream_t st, uint8_t* filter_table, long long* phase, int reserved_sms,
+                                   const FusedFinalize* fin, bool* fused_out);
 
 }  // namespace sinc

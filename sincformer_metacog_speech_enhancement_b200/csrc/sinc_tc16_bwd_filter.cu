@@ -30,6 +30,11 @@
 #include <cstdlib>
 #include <type_traits>
 
+#include <atomic>
+#include <cstdio>
+#include <chrono>
+
+#include "sinc_finalize.cuh"
 #include "sinc_internal.h"
 #include "sinc_synth.cuh"
 #include "sinc_tc.cuh"
@@ -68,7 +73,8 @@ constexpr int F2_GSTAGE_BYTES = 64 * F2_GPITCH;
 constexpr int F2_SM_G = 0;                  // [F2_GSTAGES][64 rows][F2_GPITCH]
 constexpr int F2_SM_X = F2_SM_G + F2_GSTAGES * F2_GSTAGE_BYTES;  // [buf 2][rho 4][hi/mid 2][F2_XLEN] bf16
 constexpr int F2_SM_BAR = F2_SM_X + 2 * 8 * F2_XLEN * 2;
-constexpr int F2_SM_TOTAL = F2_SM_BAR + 512;
+constexpr int F2_SM_FIN = F2_SM_BAR + 512;  // fused finalize (doubles): us[256] chi[256] clo[256] Gs[256] part[2][256] scratch[64]
+constexpr int F2_SM_TOTAL = F2_SM_FIN + (6 * 256 + 64) * 8;
 static_assert(28 + F2_GSTAGES <= 32, "barrier table: tmem_slot lives at bars + 32");
 static_assert((F2_XLEN * 2) % 16 == 0, "waveform copies must stay 16-byte aligned");
 
@@ -105,6 +111,14 @@ struct BwdFilterTc16Args {
   long long* phase;  // diagnostic time stamps (CTA 0), may be null
   Bank bank;         // only read when tab != nullptr
   uint8_t* tab;      // filter table for the grad-input kernel (sinc_synth.cuh), or nullptr
+  // Fused finalize (one filter block, C <= 64): after its last flush every CTA announces its partial tile on a tagged
+  // counter in the workspace; CTA c < C waits for all of them, reduces column c of every tile in fp64 in a fixed order
+  // and applies the synthesis chain rule (sinc_finalize.cuh) -- no second launch, no second ramp-up.
+  unsigned long long* fin_sync;  // {tag : 40 | arrivals : 24}, or nullptr: the caller launches finalize_kernel instead
+  unsigned long long fin_tag;    // unique per launch (host counter): stale contents of the word never match it
+  float* grad_low;
+  float* grad_band;
+  float* grad_filters;           // debug output [C][K], may be null
 #ifdef SINC_ABLATION
   int ablate;        // experiment build only (tools/gf_overlap_repro.py): bit 3 = the issuers do NOT wait for the previous
                      // window's flush (the overlap under investigation), bit 4 = the flush warps release the accumulator
@@ -140,6 +154,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     a.phase[0] = clock64();
     a.phase[1] = (long long)tc::global_timer_ns();
   }
+#ifdef SINC_ABLATION
+  const uint64_t dbg_start = tc::global_timer_ns();
+#endif
   uint16_t* xs = reinterpret_cast<uint16_t*>(smem + F2_SM_X);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + F2_SM_BAR);
   uint64_t* a_full = bars;            // [F2_RING]  producers (4 warps of one group) -> issuers
@@ -152,6 +169,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   uint64_t* g_empty = bars + 28;      // [F2_GSTAGES]  converters (8 warps) -> copy issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);  // after g_empty[F2_GSTAGES]
   uint8_t* gst = smem + F2_SM_G;
+  double* fin_us = reinterpret_cast<double*>(smem + F2_SM_FIN);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C = a.C, H = (a.K - 1) / 2;
@@ -502,6 +520,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           reinterpret_cast<uint32_t*>(a.tab)[i] = tab_header_word(a.bank, i);
       for (int c = 4 * blockIdx.x + (warp - 12); c < 64; c += 4 * gridDim.x) tab_write_row(a.bank, a.tab, c, lane);
     }
+    if (a.fin_sync && (int)blockIdx.x < C)  // the G-independent factors of this CTA's filter (read in the tail, below)
+      finalize_factors(a.bank, chan_coef(a.bank, blockIdx.x), tid - 384, 128, fin_us, fin_us + 256, fin_us + 512);
     const int quarter = warp & 3;
     const int m = 32 * quarter + lane;
     const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
@@ -544,6 +564,136 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     a.phase[4] = clock64();
     a.phase[5] = (long long)tc::global_timer_ns();
   }
+  if (!a.fin_sync) return;
+#ifdef SINC_ABLATION
+  const uint64_t dbg_t0 = tc::global_timer_ns();
+  uint64_t dbg_t1 = 0, dbg_t2 = 0;
+  if (tid == 0 && GABL(6)) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("cta %d sm %u start %llu mainend %llu\n", (int)blockIdx.x, smid, (unsigned long long)dbg_start, (unsigned long long)dbg_t0);
+  }
+#endif
+
+  // ------------- fused finalize ------------------------------------------------------------------------------------
+  // The partial tile of this CTA is complete (the __syncthreads above orders the flush warps' stores before thread 0's
+  // fence).  Arrival is a CAS on {tag, count}: whatever the word held before this launch -- zero, or the garbage of a
+  // fresh workspace -- is replaced by {tag, 1} by the first CTA to arrive.  Finalising CTAs count themselves a second
+  // time once they are past the wait, and the last of them writes zero: a replay of the same launch (CUDA graph, same
+  // tag) starts from a word that does not carry its tag.
+  const unsigned long long cnt_mask = (1ull << 24) - 1;
+  const unsigned long long nfin = (unsigned long long)(C < (int)gridDim.x ? C : (int)gridDim.x);
+  if (tid == 0) {
+    __threadfence();
+    // Fast path: the word already carries this launch's tag -> one fire-and-forget add.  (A CAS per arrival turns 148
+    // CTAs finishing within microseconds of each other into a retry storm on one L2 line: measured 35 us.)  Only the
+    // first arrivals of a launch find a foreign word and race to replace it; the losers see the tag and add.
+    unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a.fin_sync);
+    for (;;) {
+      if ((old >> 24) == a.fin_tag) {
+        atomicAdd(a.fin_sync, 1ull);
+        break;
+      }
+      const unsigned long long prev = atomicCAS(a.fin_sync, old, (a.fin_tag << 24) | 1ull);
+      if (prev == old) break;
+      old = prev;
+    }
+  }
+  if ((int)blockIdx.x >= C) return;   // CTAs beyond the filter count are done: their SMs go to the next kernel
+  if (tid == 0) {
+    const uint64_t t0 = tc::global_timer_ns();
+    for (;;) {
+      unsigned long long v;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(a.fin_sync) : "memory");
+      if ((v >> 24) == a.fin_tag && (v & cnt_mask) >= (unsigned long long)gridDim.x) break;
+      __nanosleep(64);
+      if (tc::global_timer_ns() - t0 > tc::kWaitLimitNs) __trap();   // loud, like every other wait of this kernel
+    }
+    __threadfence();
+#ifdef SINC_ABLATION
+    dbg_t1 = tc::global_timer_ns();
+#endif
+    const unsigned long long before = atomicAdd(a.fin_sync, 1ull);
+    if ((before & cnt_mask) == (unsigned long long)gridDim.x + nfin - 1) atomicExch(a.fin_sync, 0ull);
+  }
+  __syncthreads();
+  {
+    double* us = fin_us;
+    double* chi = fin_us + 256;
+    double* clo = fin_us + 512;
+    double* Gs = fin_us + 768;
+    double* part = fin_us + 1024;   // [2][256]
+    double* scratch = fin_us + 1536;
+    const int K = a.K, slots = gridDim.x;
+    for (int c = blockIdx.x; c < C; c += gridDim.x) {
+      const ChanCoef cc = chan_coef(a.bank, c);
+      if (c != (int)blockIdx.x) {   // grids smaller than the filter count: later filters get their factors here
+        __syncthreads();
+        if (tid >= 384) finalize_factors(a.bank, cc, tid - 384, 128, us, chi, clo);
+      }
+      // Thread (q, e) sums element e of the filter's two tile rows over the slots q, q + 2, ...: a warp reads 128
+      // contiguous bytes per slot (indexing by tap instead scatters a warp over eight 32-byte sectors: 8 us).
+      // tile layout (see the flush warps): row (c, h), column rho * 32 + n holds tap k = 8n + rho + 4h
+      const int q = tid >> 8, e = tid & 255;
+      const int k = 8 * (e & 31) + ((e >> 5) & 3) + 4 * (e >> 7);
+      if (k < K) {
+        const float* p = a.partials + (size_t)(2 * c) * F2_DCOLS + e;
+        const size_t stride = (size_t)128 * F2_DCOLS;
+        // written by other CTAs of this launch: L2 loads (ld.global.cg), never .nc.  All loads of a batch are issued
+        // before the first add (32 in flight per thread); eight fixed fp64 chains: bitwise reproducible.
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
+        int sl = q;
+        for (; sl + 62 < slots; sl += 64) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __ldcg(p + (size_t)(sl + 2 * i) * stride);
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            s0 += (double)v[i];
+            s1 += (double)v[i + 1];
+            s2 += (double)v[i + 2];
+            s3 += (double)v[i + 3];
+            s4 += (double)v[i + 4];
+            s5 += (double)v[i + 5];
+            s6 += (double)v[i + 6];
+            s7 += (double)v[i + 7];
+          }
+        }
+        for (; sl + 14 < slots; sl += 16) {
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __ldcg(p + (size_t)(sl + 2 * i) * stride);
+          s0 += (double)v[0];
+          s1 += (double)v[1];
+          s2 += (double)v[2];
+          s3 += (double)v[3];
+          s4 += (double)v[4];
+          s5 += (double)v[5];
+          s6 += (double)v[6];
+          s7 += (double)v[7];
+        }
+        for (; sl < slots; sl += 2) s0 += (double)__ldcg(p + (size_t)sl * stride);
+        part[q * 256 + k] = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+      }
+      __syncthreads();
+      if (tid < K) {
+        const double s = part[tid] + part[256 + tid];
+        Gs[tid] = s;
+        if (a.grad_filters) a.grad_filters[(size_t)c * K + tid] = (float)s;
+      }
+      __syncthreads();
+#ifdef SINC_ABLATION
+      if (tid == 0) dbg_t2 = tc::global_timer_ns();
+#endif
+      finalize_chain_rule<F2_THREADS>(a.bank, cc, c, Gs, us, chi, clo, scratch, a.grad_low, a.grad_band);
+    }
+  }
+#ifdef SINC_ABLATION
+  if (tid == 0 && GABL(5) && (blockIdx.x == 0 || blockIdx.x == 63))
+    printf("gf tail cta %d: wait %llu ns, reduce %llu ns, chain rule %llu ns\n", (int)blockIdx.x,
+           (unsigned long long)(dbg_t1 - dbg_t0), (unsigned long long)(dbg_t2 - dbg_t1),
+           (unsigned long long)(tc::global_timer_ns() - dbg_t2));
+#endif
 }
 
 bool tc16_bwd_filter_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
@@ -559,7 +709,8 @@ size_t tc16_bwd_filter_partial_bytes(int C) {
 
 cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_stride_b, const void* gy, int gy_dtype,
                                    float* ws_partials, int* slots_used, int64_t B, int64_t T, const DeviceInfo& di,
-                                   cudaStream_t st, uint8_t* filter_table, long long* phase, int reserved_sms) {
+                                   cudaStream_t st, uint8_t* filter_table, long long* phase, int reserved_sms,
+                                   const FusedFinalize* fin, bool* fused_out) {
   BwdFilterTc16Args a;
   a.x = x;
   a.xsb = x_stride_b;
@@ -575,6 +726,20 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
   a.phase = phase ? phase + 12 : nullptr;  // sinc_options.phase_stamps (diagnostic, normally null)
   a.bank = bank;
   a.tab = (bank.C <= 64 && bank.K <= 256) ? filter_table : nullptr;
+  a.fin_sync = nullptr;
+  a.fin_tag = 0;
+  a.grad_low = a.grad_band = a.grad_filters = nullptr;
+  if (fin && fin->sync_word && a.nblk == 1) {
+    // launch tags: a process-wide counter started from the clock, 40 bits -- never repeats within a process, and neither
+    // zero-filled nor small-integer garbage in a fresh workspace looks like one
+    static std::atomic<unsigned long long> next_tag{
+        (unsigned long long)std::chrono::steady_clock::now().time_since_epoch().count() * 0x9E3779B97F4A7C15ull};
+    a.fin_sync = fin->sync_word;
+    a.fin_tag = (next_tag.fetch_add(1) & ((1ull << 39) - 1)) | (1ull << 39);   // never zero
+    a.grad_low = fin->grad_low;
+    a.grad_band = fin->grad_band;
+    a.grad_filters = fin->grad_filters;
+  }
 #ifdef SINC_ABLATION
   a.ablate = getenv("SINC_ABLATE_GF") ? atoi(getenv("SINC_ABLATE_GF")) : 0;
 #endif
@@ -590,6 +755,7 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
   kern<<<grid, F2_THREADS, smem, st>>>(a);
   count_launch();
   *slots_used = (int)per_blk;
+  if (fused_out) *fused_out = a.fin_sync != nullptr;
   return cudaGetLastError();
 }
 

@@ -77,7 +77,7 @@ def test_install_into_real_perception_agent(perception):
             assert len(out) == 3
             sum((o * g.to(dev())).sum() for o, g in zip(out, gz)).backward()
             torch.cuda.synchronize()
-        assert sb.kernel_launch_count() - n0 >= 3                              # forward, grad-filter, finalize: our kernels ran
+        assert sb.kernel_launch_count() - n0 >= 2                              # forward, grad-filter (+ fused finalize): our kernels ran
         assert rec["fwd"] == "tc16" and rec["bwd_filter"] == "tc16" and "bwd_input" not in rec   # the waveform is data
         for name, o, o32, o64 in zip(("z_real", "z_imag", "sigma"), out, out32, out64):
             assert o.shape == o32.shape
