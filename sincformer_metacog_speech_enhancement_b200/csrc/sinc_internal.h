@@ -48,6 +48,23 @@ uint64_t launch_count();
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of once per launch
 cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
 
+// Launch with programmatic stream serialisation allowed (see sinc_tc.cuh: griddep_wait / griddep_launch).  The kernel MUST
+// execute griddepcontrol.wait before its first global-memory access.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int threads, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---- tiling constants shared between workspace sizing and the kernels -------------------------
 constexpr int kChanBlock = 64;    // channels handled per CTA (filters kept in shared memory)
 constexpr int kTapBlock = 256;    // taps handled per grad-filter CTA

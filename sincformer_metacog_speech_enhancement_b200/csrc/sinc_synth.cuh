@@ -189,6 +189,47 @@ __device__ __noinline__ void synth_two_filters_warp(const Bank& bk, int ca, int 
   }
 }
 
+// One filter per call, written to a row in SHARED memory, with a small code footprint: every loop is a real loop (no
+// unrolling) and there is ONE expansion of cosf / sinf.  A prologue runs its synthesis code exactly once per warp, so
+// what it costs is mostly the instruction fetch of code that is not in any cache yet (ncu r02z, forward kernel: the
+// 1356 straight-line instructions of the two-filters-side-by-side version accounted for 63 % `no_inst` stalls, ~180
+// cycles per 128-byte line, 40k cycles of prologue in a 200k-cycle kernel).  Same arithmetic in the same order as
+// synth_filter_warp: bit-identical taps.  Returns max |w_k| (all lanes).
+static __device__ __noinline__ float synth_filter_row_compact(const Bank& bk, int c, int lane, float* row) {
+  const int K = bk.K;
+  const int H = (K - 1) / 2;
+  const ChanCoef cc = chan_coef(bk, c);
+  const float fs = (float)(0.5 * (cc.f_hi + cc.f_lo));
+  const float fd = (float)(0.5 * (cc.f_hi - cc.f_lo));
+  double sumabs = 0.0;
+#pragma unroll 1
+  for (int j = lane; j < H; j += 32) {
+    const float nj = bk.n[j];
+    const float left = __fdividef(2.0f * cosf(fs * nj) * sinf(fd * nj), nj * 0.5f + 1e-8f);
+    const float l = left * bk.window[j], rr = left * bk.window[K - 1 - j];
+    sumabs += (double)fabsf(l) + (double)fabsf(rr);
+    row[j] = l;
+    row[K - 1 - j] = rr;
+  }
+  const float uc = (float)(2.0 * (cc.f_hi - cc.f_lo)) * bk.window[H];
+  if (lane == 0) {
+    sumabs += (double)fabsf(uc);
+    row[H] = uc;
+  }
+  const double rS = 1.0 / (warp_sum(sumabs) + 1e-8);
+  __syncwarp();
+  float mx = 0.f;
+#pragma unroll 1
+  for (int k = lane; k < K; k += 32) {
+    const float w = (float)((double)row[k] * rS);
+    row[k] = w;
+    mx = fmaxf(mx, fabsf(w));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  return mx;
+}
+
 // ---- filter table in the workspace -----------------------------------------------------------------------------
 // The grad-filter kernel (16-bit tcgen05 engine) has idle warps at its start; they synthesise the filters ONCE and
 // leave them in the workspace, so that the grad-input kernel -- launched later on the same stream -- does not spend

@@ -58,6 +58,13 @@ __device__ __forceinline__ void tmem_relinquish() {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+// Programmatic dependent launch (the three persistent 16-bit kernels are launched with the stream-serialisation attribute,
+// sinc_internal.h: launch_pdl): griddep_wait() returns when every kernel this one depends on has completed and its memory
+// is visible -- nothing that reads or writes global memory may come before it; griddep_launch() lets the NEXT kernel on
+// the stream be set up and its CTAs take the SMs as ours leave them (they sit in their own griddep_wait until this grid is
+// complete), which takes the ~4 us of launch processing off the critical path between two of our kernels.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy writes to shared memory -> visible to the async proxy (tensor core / bulk copy reads)

@@ -204,6 +204,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+  tc::griddep_wait();     // everything above touched shared memory and TMEM only
+  tc::griddep_launch();
 
   // contiguous range of tiles for this CTA (tile = 512 samples of one utterance)
   const int64_t tile_begin = a.ntiles * slot / per_blk;
@@ -688,6 +690,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
       finalize_chain_rule<F2_THREADS>(a.bank, cc, c, Gs, us, chi, clo, scratch, a.grad_low, a.grad_band);
     }
   }
+  if (blockIdx.x == 0 && tid == 0 && a.phase) a.phase[7] = (long long)tc::global_timer_ns();   // end of the fused finalize
 #ifdef SINC_ABLATION
   if (tid == 0 && GABL(5) && (blockIdx.x == 0 || blockIdx.x == 63))
     printf("gf tail cta %d: wait %llu ns, reduce %llu ns, chain rule %llu ns\n", (int)blockIdx.x,
@@ -752,7 +755,8 @@ cudaError_t launch_bwd_filter_tc16(const Bank& bank, const float* x, int64_t x_s
   auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_filter_tc16_kernel<true> : bwd_filter_tc16_kernel<false>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, F2_THREADS, smem, st>>>(a);
+  e = launch_pdl(kern, grid, F2_THREADS, smem, st, a);
+  if (e != cudaSuccess) return e;
   count_launch();
   *slots_used = (int)per_blk;
   if (fused_out) *fused_out = a.fin_sync != nullptr;

@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   for (int i = tid; i < H2_SM_BAR / 16; i += H2_THREADS)
     reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
+  tc::griddep_wait();     // everything above touched shared memory, TMEM and the (parameter-space) tensor map only
+  tc::griddep_launch();
   {
     float* wst = reinterpret_cast<float*>(ring);  // fp32 filters [c][256], rows >= C and taps >= K stay zero
     // The filters come from the table the grad-filter kernel left in the workspace when that table provably belongs
@@ -669,7 +671,8 @@ cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype
   CUtensorMap gmap;
   memset(&gmap, 0, sizeof(gmap));
   if (!make_grad_map(&gmap, gy, gy_dtype == SINC_DTYPE_BF16, B, bank.C, T)) return cudaErrorNotSupported;
-  kern<<<grid, H2_THREADS, smem, st>>>(a, gmap);
+  e = launch_pdl(kern, grid, H2_THREADS, smem, st, a, gmap);
+  if (e != cudaSuccess) return e;
   count_launch();
   return cudaGetLastError();
 }

@@ -146,53 +146,54 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
     tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
+  tc::griddep_wait();     // everything above touched shared memory and TMEM only
+  tc::griddep_launch();
   float* wsc = stage;  // fp32 filters [16][U_WPITCH], zero outside [0, K)
   for (int i = tid; i < U_FB * U_WPITCH; i += U_THREADS) wsc[i] = 0.f;
   __syncthreads();
-  if (FABL(4)) {   // experiment: the round-1 prologue (one filter per warp call, two rounds on 11 warps)
-    for (int cl = warp; cl < U_FB; cl += U_THREADS / 32) {
-      const int c = c0 + cl;
-      float mx = 0.f;
-      if (c < C)
-        synth_filter_warp(a.bank, c, lane, [&](int k, double w) {
+  if (FABL(4)) {   // experiment (A/B): two filters side by side per warp, fully unrolled -- 1356 instructions run once
+    if (warp < U_FB / 2) {
+      const int cl2[2] = {2 * warp, 2 * warp + 1};
+      float mx[2] = {0.f, 0.f};
+      const bool va = c0 + cl2[0] < C, vb = c0 + cl2[1] < C;
+      auto put = [&](int f) {
+        return [&, f](int k, double w) {
           const float wf = (float)w;
-          wsc[cl * U_WPITCH + k] = wf;
-          mx = fmaxf(mx, fabsf(wf));
-        });
+          wsc[cl2[f] * U_WPITCH + k] = wf;
+          mx[f] = fmaxf(mx[f], fabsf(wf));
+        };
+      };
+      if (va && vb) {
+        synth_two_filters_warp(a.bank, c0 + cl2[0], c0 + cl2[1], lane, put(0), put(1));
+      } else if (va) {
+        synth_filter_warp(a.bank, c0 + cl2[0], lane, put(0));
+      }
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const int se = u_scale_exp(mx);
+      for (int f = 0; f < 2; ++f) {
+        float m = mx[f];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const int se = u_scale_exp(m);
+        if (lane == 0) winv[cl2[f]] = u_pow2(-se);
+        const float sw = u_pow2(se);
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) wsc[cl2[f] * U_WPITCH + k] *= sw;  // exact (power of two)
+      }
+    }
+  } else if (warp < U_FB / 2) {
+    // warps 0-7: two filters each, one after the other through ONE small loop body (sinc_synth.cuh: the cost of a
+    // prologue is the instruction fetch of cold code, not its arithmetic)
+#pragma unroll 1
+    for (int f = 0; f < 2; ++f) {
+      const int cl = 2 * warp + f;
+      float* row = wsc + cl * U_WPITCH;
+      const float m = c0 + cl < C ? synth_filter_row_compact(a.bank, c0 + cl, lane, row) : 0.f;
+      const int se = u_scale_exp(m);
       if (lane == 0) winv[cl] = u_pow2(-se);
       const float sw = u_pow2(se);
       __syncwarp();
-      for (int k = lane; k < K; k += 32) wsc[cl * U_WPITCH + k] *= sw;
-    }
-  } else if (warp < U_FB / 2) {  // warps 0-7: two filters each, synthesised side by side (sinc_synth.cuh) -- one round
-    const int cl2[2] = {2 * warp, 2 * warp + 1};
-    float mx[2] = {0.f, 0.f};
-    const bool va = c0 + cl2[0] < C, vb = c0 + cl2[1] < C;
-    auto put = [&](int f) {
-      return [&, f](int k, double w) {
-        const float wf = (float)w;
-        wsc[cl2[f] * U_WPITCH + k] = wf;
-        mx[f] = fmaxf(mx[f], fabsf(wf));
-      };
-    };
-    if (va && vb) {
-      synth_two_filters_warp(a.bank, c0 + cl2[0], c0 + cl2[1], lane, put(0), put(1));
-    } else if (va) {
-      synth_filter_warp(a.bank, c0 + cl2[0], lane, put(0));
-    }
-#pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      float m = mx[f];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-      const int se = u_scale_exp(m);
-      if (lane == 0) winv[cl2[f]] = u_pow2(-se);
-      const float sw = u_pow2(se);
-      __syncwarp();
-      for (int k = lane; k < K; k += 32) wsc[cl2[f] * U_WPITCH + k] *= sw;  // exact (power of two)
+#pragma unroll 1
+      for (int k = lane; k < K; k += 32) row[k] *= sw;  // exact (power of two)
     }
   }
   tc::fence_before_sync();
@@ -482,7 +483,8 @@ cudaError_t launch_fwd_tc16(const Bank& bank, const float* x, int64_t x_stride_b
   if (gn_partial && y_dtype != SINC_DTYPE_F32) return cudaErrorInvalidValue;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, U_THREADS, smem, st>>>(a);
+  e = launch_pdl(kern, grid, U_THREADS, smem, st, a);
+  if (e != cudaSuccess) return e;
   count_launch();
   return cudaGetLastError();
 }
