@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   uint64_t* d_empty = bars + 22;      // [2]  flush warps (4) -> issuers
   uint64_t* g_full = bars + 24;       // [F2_GSTAGES]  bulk copies (expect_tx) -> converters
   uint64_t* g_empty = bars + 28;      // [F2_GSTAGES]  converters (8 warps) -> copy issuer
+  uint64_t* fin_bar = bars + 12;      // fused finalize: bulk copies of the partial tiles -> the whole CTA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);  // after g_empty[F2_GSTAGES]
   uint8_t* gst = smem + F2_SM_G;
   double* fin_us = reinterpret_cast<double*>(smem + F2_SM_FIN);
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
       tc::mbar_init(&g_full[i], 1);
       tc::mbar_init(&g_empty[i], 8);
     }
+    tc::mbar_init(fin_bar, 1);
     tc::mbar_init_fence();
   }
   if (warp == 8) {
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
   if (!a.fin_sync) return;
 #ifdef SINC_ABLATION
   const uint64_t dbg_t0 = tc::global_timer_ns();
-  uint64_t dbg_t1 = 0, dbg_t2 = 0;
+  uint64_t dbg_t1 = 0, dbg_t2 = 0, dbg_ta = 0, dbg_tb = 0, dbg_tc = 0;
   if (tid == 0 && GABL(6)) {
     uint32_t smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -615,8 +617,6 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
 #ifdef SINC_ABLATION
     dbg_t1 = tc::global_timer_ns();
 #endif
-    const unsigned long long before = atomicAdd(a.fin_sync, 1ull);
-    if ((before & cnt_mask) == (unsigned long long)gridDim.x + nfin - 1) atomicExch(a.fin_sync, 0ull);
   }
   __syncthreads();
   {
@@ -627,56 +627,86 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     double* part = fin_us + 1024;   // [2][256]
     double* scratch = fin_us + 1536;
     const int K = a.K, slots = gridDim.x;
+    uint32_t fin_parity = 0;
     for (int c = blockIdx.x; c < C; c += gridDim.x) {
       const ChanCoef cc = chan_coef(a.bank, c);
       if (c != (int)blockIdx.x) {   // grids smaller than the filter count: later filters get their factors here
         __syncthreads();
         if (tid >= 384) finalize_factors(a.bank, cc, tid - 384, 128, us, chi, clo);
       }
-      // Thread (q, e) sums element e of the filter's two tile rows over the slots q, q + 2, ...: a warp reads 128
-      // contiguous bytes per slot (indexing by tap instead scatters a warp over eight 32-byte sectors: 8 us).
+      // The filter's two rows of every partial tile (1 KB, contiguous) come into shared memory with one bulk copy per
+      // slot, all in flight at once: ONE L2 round trip instead of a chain of dependent load batches (measured 1.1 - 1.7 us
+      // per batch of 16 - 32 loads per thread, 5.5 - 8 us in total).  The staging ring and the waveform buffers are idle now.
+      // Thread (q, e) then sums element e over the slots q, q + 2, ... in eight fixed fp64 chains: bitwise reproducible.
       // tile layout (see the flush warps): row (c, h), column rho * 32 + n holds tap k = 8n + rho + 4h
       const int q = tid >> 8, e = tid & 255;
       const int k = 8 * (e & 31) + ((e >> 5) & 3) + 4 * (e >> 7);
+      const float* src = a.partials + (size_t)(2 * c) * F2_DCOLS;
+      const size_t stride = (size_t)128 * F2_DCOLS;
+      const bool staged = slots * 1024 <= F2_SM_BAR;
+      if (staged) {
+        // generic -> async proxy: the partial tiles were written with ordinary stores (made visible by the arrival protocol
+        // above), the copies below read them through the async proxy; shared memory changes hands as well.  The copies
+        // may complete before thread 0 has posted the byte count: the transaction count of an mbarrier may run negative.
+        if (tid == 0) tc::mbar_expect_tx(fin_bar, (uint32_t)slots * 1024u);
+        if (tc::elect_one()) {
+          asm volatile("fence.proxy.async;" ::: "memory");
+          const uint32_t bar = tc::smem_addr(fin_bar);
+          for (int sl = warp; sl < slots; sl += F2_THREADS / 32)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             tc::smem_addr(smem) + (uint32_t)sl * 1024u),
+                         "l"(src + (size_t)sl * stride), "r"(1024u), "r"(bar)
+                         : "memory");
+        }
+#ifdef SINC_ABLATION
+        if (tid == 0) dbg_ta = tc::global_timer_ns();
+#endif
+        ok = ok && tc::mbar_wait(fin_bar, fin_parity);
+        fin_parity ^= 1u;
+#ifdef SINC_ABLATION
+        if (tid == 0) dbg_tb = tc::global_timer_ns();
+#endif
+      }
       if (k < K) {
-        const float* p = a.partials + (size_t)(2 * c) * F2_DCOLS + e;
-        const size_t stride = (size_t)128 * F2_DCOLS;
-        // written by other CTAs of this launch: L2 loads (ld.global.cg), never .nc.  All loads of a batch are issued
-        // before the first add (32 in flight per thread); eight fixed fp64 chains: bitwise reproducible.
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
-        int sl = q;
-        for (; sl + 62 < slots; sl += 64) {
-          float v[32];
+        if (staged) {
+          const float* p = reinterpret_cast<const float*>(smem) + e;
+#pragma unroll 1
+          for (int sl = q; sl < slots; sl += 16) {
+            float v[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __ldcg(p + (size_t)(sl + 2 * i) * stride);
+            for (int i = 0; i < 8; ++i) v[i] = sl + 2 * i < slots ? p[(sl + 2 * i) * 256] : 0.f;
+            s0 += (double)v[0];
+            s1 += (double)v[1];
+            s2 += (double)v[2];
+            s3 += (double)v[3];
+            s4 += (double)v[4];
+            s5 += (double)v[5];
+            s6 += (double)v[6];
+            s7 += (double)v[7];
+          }
+        } else {   // more partial tiles than shared memory holds (not on a 148-SM part): L2 loads (ld.global.cg), never .nc
+          const float* p = src + e;
+#pragma unroll 1
+          for (int sl = q; sl < slots; sl += 16) {
+            float v[8];
 #pragma unroll
-          for (int i = 0; i < 32; i += 8) {
-            s0 += (double)v[i];
-            s1 += (double)v[i + 1];
-            s2 += (double)v[i + 2];
-            s3 += (double)v[i + 3];
-            s4 += (double)v[i + 4];
-            s5 += (double)v[i + 5];
-            s6 += (double)v[i + 6];
-            s7 += (double)v[i + 7];
+            for (int i = 0; i < 8; ++i) v[i] = sl + 2 * i < slots ? __ldcg(p + (size_t)(sl + 2 * i) * stride) : 0.f;
+            s0 += (double)v[0];
+            s1 += (double)v[1];
+            s2 += (double)v[2];
+            s3 += (double)v[3];
+            s4 += (double)v[4];
+            s5 += (double)v[5];
+            s6 += (double)v[6];
+            s7 += (double)v[7];
           }
         }
-        for (; sl + 14 < slots; sl += 16) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __ldcg(p + (size_t)(sl + 2 * i) * stride);
-          s0 += (double)v[0];
-          s1 += (double)v[1];
-          s2 += (double)v[2];
-          s3 += (double)v[3];
-          s4 += (double)v[4];
-          s5 += (double)v[5];
-          s6 += (double)v[6];
-          s7 += (double)v[7];
-        }
-        for (; sl < slots; sl += 2) s0 += (double)__ldcg(p + (size_t)sl * stride);
         part[q * 256 + k] = ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
       }
+#ifdef SINC_ABLATION
+      if (tid == 0) dbg_tc = tc::global_timer_ns();
+#endif
       __syncthreads();
       if (tid < K) {
         const double s = part[tid] + part[256 + tid];
@@ -690,11 +720,17 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
       finalize_chain_rule<F2_THREADS>(a.bank, cc, c, Gs, us, chi, clo, scratch, a.grad_low, a.grad_band);
     }
   }
+  if (tid == 0) {   // past the wait and done: count this CTA a second time; the last one leaves the word at zero (off the critical path)
+    const unsigned long long before = atomicAdd(a.fin_sync, 1ull);
+    if ((before & cnt_mask) == (unsigned long long)gridDim.x + nfin - 1) atomicExch(a.fin_sync, 0ull);
+  }
   if (blockIdx.x == 0 && tid == 0 && a.phase) a.phase[7] = (long long)tc::global_timer_ns();   // end of the fused finalize
 #ifdef SINC_ABLATION
   if (tid == 0 && GABL(5) && (blockIdx.x == 0 || blockIdx.x == 63))
-    printf("gf tail cta %d: wait %llu ns, reduce %llu ns, chain rule %llu ns\n", (int)blockIdx.x,
+    printf("gf tail cta %d: wait %llu ns, reduce %llu ns (issue %llu, land %llu, sum %llu, combine %llu), chain rule %llu ns\n", (int)blockIdx.x,
            (unsigned long long)(dbg_t1 - dbg_t0), (unsigned long long)(dbg_t2 - dbg_t1),
+           (unsigned long long)(dbg_ta - dbg_t1), (unsigned long long)(dbg_tb - dbg_ta), (unsigned long long)(dbg_tc - dbg_tb),
+           (unsigned long long)(dbg_t2 - dbg_tc),
            (unsigned long long)(tc::global_timer_ns() - dbg_t2));
 #endif
 }

@@ -34,6 +34,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     print(json.dumps({"ms": round(e0.elapsed_time(e1) / n, 4), "sum": float(gp.double().abs().sum())}))
 else:
     plans = (("timeline", {"SINC_ABLATE_GF": "96"}, 1),) if "--timeline" in sys.argv else None
+    if "--tail" in sys.argv:
+        plans = (("fused, tail timing", {"SINC_ABLATE_GF": "32"}, 3),)
     for label, env, n in plans or (("fused", {}, 20), ("separate finalize_kernel", {"SINC_SPLIT_FINALIZE": "1"}, 20),
                           ("fused, tail timing (one launch after warm-up)", {"SINC_ABLATE_GF": "32"}, 2),
                           ("fused, no flush guard", {"SINC_ABLATE_GF": "8"}, 20),
