@@ -107,129 +107,6 @@ __device__ __noinline__ void synth_filter_warp(const Bank& bk, int c, int lane, 
   if (lane == 0) emit(H, (double)uc * rS);
 }
 
-// Two filters per warp, interleaved: the synthesis of one filter is a chain of dependent latencies (parameter loads, fp64
-// scalar set-up, cosf / sinf, the fp64 warp reduction, one fp64 reciprocal: ~7k cycles for ~800 instructions), so a warp
-// that runs two independent instances side by side finishes both in little more than the time of one.  The forward
-// kernel's prologue uses this to synthesise its 16 filters in ONE round on 8 warps instead of two rounds on 11.
-// Same arithmetic, same order per filter as synth_filter_warp (bit-identical results).
-template <class EmitA, class EmitB>
-__device__ __noinline__ void synth_two_filters_warp(const Bank& bk, int ca, int cb, int lane, EmitA emit_a, EmitB emit_b) {
-  const int K = bk.K;
-  const int H = (K - 1) / 2;
-  const ChanCoef cc[2] = {chan_coef(bk, ca), chan_coef(bk, cb)};
-  float fs[2], fd[2];
-#pragma unroll
-  for (int f = 0; f < 2; ++f) {
-    fs[f] = (float)(0.5 * (cc[f].f_hi + cc[f].f_lo));
-    fd[f] = (float)(0.5 * (cc[f].f_hi - cc[f].f_lo));
-  }
-  auto left32 = [&](int f, float nj) -> float {
-    return __fdividef(2.0f * cosf(fs[f] * nj) * sinf(fd[f] * nj), nj * 0.5f + 1e-8f);
-  };
-  constexpr int R = 4;  // taps cached in registers per lane: covers H <= 128 (K <= 257)
-  float ul[2][R], ur[2][R];
-  double sumabs[2] = {0.0, 0.0};
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int j = r * 32 + lane;
-    const bool in = j < H;
-    const float nj = in ? bk.n[j] : 0.f;
-    const float wl = in ? bk.window[j] : 0.f, wr = in ? bk.window[K - 1 - j] : 0.f;
-#pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      float l = 0.f, rr = 0.f;
-      if (in) {
-        const float left = left32(f, nj);
-        l = left * wl;
-        rr = left * wr;
-        sumabs[f] += (double)fabsf(l) + (double)fabsf(rr);
-      }
-      ul[f][r] = l;
-      ur[f][r] = rr;
-    }
-  }
-  for (int j = R * 32 + lane; j < H; j += 32) {  // long filters: second pass recomputes these
-    const float nj = bk.n[j];
-#pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      const float left = left32(f, nj);
-      sumabs[f] += (double)fabsf(left * bk.window[j]) + (double)fabsf(left * bk.window[K - 1 - j]);
-    }
-  }
-  float uc[2];
-  double rS[2];
-#pragma unroll
-  for (int f = 0; f < 2; ++f) {
-    uc[f] = (float)(2.0 * (cc[f].f_hi - cc[f].f_lo)) * bk.window[H];
-    if (lane == 0) sumabs[f] += (double)fabsf(uc[f]);
-  }
-#pragma unroll
-  for (int f = 0; f < 2; ++f) rS[f] = 1.0 / (warp_sum(sumabs[f]) + 1e-8);
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int j = r * 32 + lane;
-    if (j < H) {
-      emit_a(j, (double)ul[0][r] * rS[0]);
-      emit_a(K - 1 - j, (double)ur[0][r] * rS[0]);
-      emit_b(j, (double)ul[1][r] * rS[1]);
-      emit_b(K - 1 - j, (double)ur[1][r] * rS[1]);
-    }
-  }
-  for (int j = R * 32 + lane; j < H; j += 32) {
-    const float nj = bk.n[j];
-    const float la = left32(0, nj), lb = left32(1, nj);
-    emit_a(j, (double)(la * bk.window[j]) * rS[0]);
-    emit_a(K - 1 - j, (double)(la * bk.window[K - 1 - j]) * rS[0]);
-    emit_b(j, (double)(lb * bk.window[j]) * rS[1]);
-    emit_b(K - 1 - j, (double)(lb * bk.window[K - 1 - j]) * rS[1]);
-  }
-  if (lane == 0) {
-    emit_a(H, (double)uc[0] * rS[0]);
-    emit_b(H, (double)uc[1] * rS[1]);
-  }
-}
-
-// One filter per call, written to a row in SHARED memory, with a small code footprint: every loop is a real loop (no
-// unrolling) and there is ONE expansion of cosf / sinf.  A prologue runs its synthesis code exactly once per warp, so
-// what it costs is mostly the instruction fetch of code that is not in any cache yet (ncu r02z, forward kernel: the
-// 1356 straight-line instructions of the two-filters-side-by-side version accounted for 63 % `no_inst` stalls, ~180
-// cycles per 128-byte line, 40k cycles of prologue in a 200k-cycle kernel).  Same arithmetic in the same order as
-// synth_filter_warp: bit-identical taps.  Returns max |w_k| (all lanes).
-static __device__ __noinline__ float synth_filter_row_compact(const Bank& bk, int c, int lane, float* row) {
-  const int K = bk.K;
-  const int H = (K - 1) / 2;
-  const ChanCoef cc = chan_coef(bk, c);
-  const float fs = (float)(0.5 * (cc.f_hi + cc.f_lo));
-  const float fd = (float)(0.5 * (cc.f_hi - cc.f_lo));
-  double sumabs = 0.0;
-#pragma unroll 1
-  for (int j = lane; j < H; j += 32) {
-    const float nj = bk.n[j];
-    const float left = __fdividef(2.0f * cosf(fs * nj) * sinf(fd * nj), nj * 0.5f + 1e-8f);
-    const float l = left * bk.window[j], rr = left * bk.window[K - 1 - j];
-    sumabs += (double)fabsf(l) + (double)fabsf(rr);
-    row[j] = l;
-    row[K - 1 - j] = rr;
-  }
-  const float uc = (float)(2.0 * (cc.f_hi - cc.f_lo)) * bk.window[H];
-  if (lane == 0) {
-    sumabs += (double)fabsf(uc);
-    row[H] = uc;
-  }
-  const double rS = 1.0 / (warp_sum(sumabs) + 1e-8);
-  __syncwarp();
-  float mx = 0.f;
-#pragma unroll 1
-  for (int k = lane; k < K; k += 32) {
-    const float w = (float)((double)row[k] * rS);
-    row[k] = w;
-    mx = fmaxf(mx, fabsf(w));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  return mx;
-}
-
 // ---- filter table in the workspace -----------------------------------------------------------------------------
 // The grad-filter kernel (16-bit tcgen05 engine) has idle warps at its start; they synthesise the filters ONCE and
 // leave them in the workspace, so that the grad-input kernel -- launched later on the same stream -- does not spend

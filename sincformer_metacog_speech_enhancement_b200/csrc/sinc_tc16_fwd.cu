@@ -27,6 +27,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -45,6 +46,20 @@ constexpr int U_XT = U_TT + U_KS;         // 1168 waveform samples per tile
 constexpr int U_PITCH = U_TT + 8;         // floats; +8 makes the phase-interleaved staging writes conflict free
 constexpr int U_WPITCH = 272;             // floats, setup scratch (one filter per row)
 constexpr int U_TM_D1 = 128, U_TM_WHI = 240, U_TM_WLO = 376;
+// Prologue scratch (inside the output staging buffers, which are idle until the main loop starts), per filter: the scaled
+// taps split into fp16 hi / lo ONCE and packed in pairs, in two alignments -- word j of the even copy holds taps
+// (2j - 8, 2j - 7), of the odd copy (2j - 9, 2j - 8); taps outside [0, K) are zero -- so that row (filter, phase r) of W'
+// is a run of consecutive words of one copy.  Offsets (32-bit words) chosen so that the 32 lanes of a warp (4 filters x 8
+// phases) read 32 distinct banks: odd copy at +164 (4 mod 32), lo copies at +328, filter pitch 648 (8 mod 32).
+constexpr int U_PLEN = 144, U_P_ODD = 164, U_P_LO = 328, U_PPITCH = 648;
+constexpr int U_SCR_P = U_FB * U_WPITCH;                 // float offset of the packed area within the scratch
+constexpr int U_SCR_N = U_SCR_P + U_FB * U_PPITCH;       // n_ [<= 144]
+constexpr int U_SCR_WIN = U_SCR_N + 144;                 // window [<= 272]
+constexpr int U_SCR_CC = U_SCR_WIN + U_KS;                // per-filter scalars (ChanCoef) [16]
+constexpr int U_SCR_END = U_SCR_CC + U_FB * 8;
+static_assert(sizeof(ChanCoef) <= 32 && (U_SCR_CC * 4) % 8 == 0, "ChanCoef slots");
+static_assert(U_P_LO + U_P_ODD + U_PLEN <= U_PPITCH && U_P_ODD >= U_PLEN && U_P_LO >= U_P_ODD + U_PLEN, "packed layout");
+static_assert((U_SCR_P * 4) % 16 == 0 && (U_FB * U_PPITCH) % 4 == 0, "the packed area is zeroed with 16-byte stores");
 
 constexpr int U_SM_X = 0;                                     // [buf 2][hi/lo 2][U_XT] fp16
 constexpr int U_SM_STAGE = U_SM_X + ((2 * 2 * U_XT * 2 + 127) / 128) * 128;
@@ -52,7 +67,7 @@ constexpr int U_NSTAGE = 3;               // output staging buffers: the bulk st
 constexpr int U_SM_SCALE = U_SM_STAGE + U_NSTAGE * U_FB * U_PITCH * 4;   // x inverse scales [4], filter inverse scales [16]
 constexpr int U_SM_BAR = U_SM_SCALE + 256;   // scale area: xinv [4], winv [16], GroupNorm warp sums [8][2]
 constexpr int U_SM_TOTAL = U_SM_BAR + 128;
-static_assert(U_FB * U_WPITCH * 4 <= U_FB * U_PITCH * 4, "setup scratch must fit in one staging buffer");
+static_assert(U_SCR_END * 4 <= U_NSTAGE * U_FB * U_PITCH * 4, "setup scratch must fit in the staging buffers");
 
 struct FwdTc16Args {
   Bank bank;
@@ -97,6 +112,60 @@ __device__ __forceinline__ void u_split_f16(float v, uint16_t& hi, uint16_t& lo)
   const __half l = __float2half_rn(v - __half2float(h));
   hi = __half_as_ushort(h);
   lo = __half_as_ushort(l);
+}
+
+// One filter of the forward prologue, whole warp: synthesis (same arithmetic and order as synth_filter_warp in sinc_synth.cuh:
+// bit-identical taps) -> power-of-two scale -> fp16 hi / lo split -> the two packed copies described at U_PLEN.  Written for
+// a small code footprint -- real loops, one expansion of cosf / sinf: a prologue runs its code exactly once per warp, and
+// what that costs is mostly the instruction fetch of code that is in no cache (ncu r02z: 63 % `no_inst` stalls in the
+// 1356 straight-line instructions of the previous version; 40k cycles of prologue in a 200k-cycle kernel).  n_ and the
+// window are read from shared-memory copies: a global load per loop iteration was ~700 cycles of exposed latency.
+static __device__ __noinline__ void u_synth_pack(int K, const ChanCoef cc, int lane, float* row, uint32_t* P, const float* n_s,
+                                                 const float* win_s, float* winv_out) {
+  const int H = (K - 1) / 2;
+  const float fs = (float)(0.5 * (cc.f_hi + cc.f_lo));
+  const float fd = (float)(0.5 * (cc.f_hi - cc.f_lo));
+  double sumabs = 0.0;
+  float mxu = 0.f;
+#pragma unroll 1
+  for (int j = lane; j < H; j += 32) {
+    const float nj = n_s[j];
+    const float left = __fdividef(2.0f * cosf(fs * nj) * sinf(fd * nj), nj * 0.5f + 1e-8f);
+    const float l = left * win_s[j], rr = left * win_s[K - 1 - j];
+    sumabs += (double)fabsf(l) + (double)fabsf(rr);
+    mxu = fmaxf(mxu, fmaxf(fabsf(l), fabsf(rr)));
+    row[j] = l;
+    row[K - 1 - j] = rr;
+  }
+  const float uc = (float)(2.0 * (cc.f_hi - cc.f_lo)) * win_s[H];
+  if (lane == 0) {
+    sumabs += (double)fabsf(uc);
+    mxu = fmaxf(mxu, fabsf(uc));
+    row[H] = uc;
+  }
+  const double rS = 1.0 / (warp_sum(sumabs) + 1e-8);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mxu = fmaxf(mxu, __shfl_xor_sync(0xffffffffu, mxu, o));
+  // max_k |w_k| with w_k = (float)((double)u_k * rS): rounding is monotonic, so it is the image of max_k |u_k|
+  const int se = u_scale_exp((float)((double)mxu * rS));
+  if (lane == 0) *winv_out = u_pow2(-se);
+  const float sw = u_pow2(se);
+  __syncwarp();
+#pragma unroll 1
+  for (int j = lane; j < U_PLEN; j += 32) {
+    const int k = 2 * j - 9;  // taps k, k+1, k+2: the odd copy's word j is (k, k+1), the even copy's (k+1, k+2)
+    uint16_t h[3], l[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int kk = k + i;
+      const float w = (kk >= 0 && kk < K) ? (float)((double)row[kk] * rS) * sw : 0.f;  // the scaling is exact
+      u_split_f16(w, h[i], l[i]);
+    }
+    P[j] = (uint32_t)h[1] | ((uint32_t)h[2] << 16);
+    P[U_P_LO + j] = (uint32_t)l[1] | ((uint32_t)l[2] << 16);
+    P[U_P_ODD + j] = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+    P[U_P_ODD + U_P_LO + j] = (uint32_t)l[0] | ((uint32_t)l[1] << 16);
+  }
 }
 
 // RG ("ragged"): T is not a multiple of 4 (fp32) / 8 (bf16) or y is not 16-byte aligned, so the rows of y do not start
@@ -146,77 +215,57 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
     tc::tmem_alloc(tmem_slot, 512);
     tc::tmem_relinquish();
   }
+  float* wsc = stage;                                            // scratch: raw taps [16][U_WPITCH]
+  uint32_t* pk = reinterpret_cast<uint32_t*>(stage + U_SCR_P);   // packed fp16 hi / lo copies [16][U_PPITCH]
+  float* n_s = stage + U_SCR_N;
+  float* win_s = stage + U_SCR_WIN;
+  for (int i = tid; i < U_FB * U_PPITCH / 4; i += U_THREADS)     // taps outside [0, K) and filters beyond C read as zero
+    reinterpret_cast<uint4*>(pk)[i] = make_uint4(0u, 0u, 0u, 0u);
   tc::griddep_wait();     // everything above touched shared memory and TMEM only
   tc::griddep_launch();
-  float* wsc = stage;  // fp32 filters [16][U_WPITCH], zero outside [0, K)
-  for (int i = tid; i < U_FB * U_WPITCH; i += U_THREADS) wsc[i] = 0.f;
+#ifdef SINC_ABLATION
+  const long long dbg_c0 = clock64();
+  long long dbg_c1 = 0, dbg_c2 = 0;
+#endif
+  // the per-filter scalars (parameter loads + an fp64 division: ~1k cycles of latency) for all 16 filters at once, next to
+  // the loads of n_ and the window, instead of at the head of every filter's synthesis
+  ChanCoef* cc_s = reinterpret_cast<ChanCoef*>(stage + U_SCR_CC);
+  if (tid >= U_THREADS - U_FB && c0 + (tid - (U_THREADS - U_FB)) < C)
+    cc_s[tid - (U_THREADS - U_FB)] = chan_coef(a.bank, c0 + (tid - (U_THREADS - U_FB)));
+  for (int i = tid; i < H; i += U_THREADS) n_s[i] = a.bank.n[i];
+  for (int i = tid; i < K; i += U_THREADS) win_s[i] = a.bank.window[i];
   __syncthreads();
-  if (FABL(4)) {   // experiment (A/B): two filters side by side per warp, fully unrolled -- 1356 instructions run once
-    if (warp < U_FB / 2) {
-      const int cl2[2] = {2 * warp, 2 * warp + 1};
-      float mx[2] = {0.f, 0.f};
-      const bool va = c0 + cl2[0] < C, vb = c0 + cl2[1] < C;
-      auto put = [&](int f) {
-        return [&, f](int k, double w) {
-          const float wf = (float)w;
-          wsc[cl2[f] * U_WPITCH + k] = wf;
-          mx[f] = fmaxf(mx[f], fabsf(wf));
-        };
-      };
-      if (va && vb) {
-        synth_two_filters_warp(a.bank, c0 + cl2[0], c0 + cl2[1], lane, put(0), put(1));
-      } else if (va) {
-        synth_filter_warp(a.bank, c0 + cl2[0], lane, put(0));
-      }
-#pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        float m = mx[f];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        const int se = u_scale_exp(m);
-        if (lane == 0) winv[cl2[f]] = u_pow2(-se);
-        const float sw = u_pow2(se);
-        __syncwarp();
-        for (int k = lane; k < K; k += 32) wsc[cl2[f] * U_WPITCH + k] *= sw;  // exact (power of two)
-      }
-    }
-  } else if (warp < U_FB / 2) {
-    // warps 0-7: two filters each, one after the other through ONE small loop body (sinc_synth.cuh: the cost of a
-    // prologue is the instruction fetch of cold code, not its arithmetic)
+  if (warp < U_FB / 2) {   // warps 0-7: two filters each, one after the other through ONE small loop body
 #pragma unroll 1
     for (int f = 0; f < 2; ++f) {
       const int cl = 2 * warp + f;
-      float* row = wsc + cl * U_WPITCH;
-      const float m = c0 + cl < C ? synth_filter_row_compact(a.bank, c0 + cl, lane, row) : 0.f;
-      const int se = u_scale_exp(m);
-      if (lane == 0) winv[cl] = u_pow2(-se);
-      const float sw = u_pow2(se);
-      __syncwarp();
-#pragma unroll 1
-      for (int k = lane; k < K; k += 32) row[k] *= sw;  // exact (power of two)
+      if (c0 + cl < C)
+        u_synth_pack(K, cc_s[cl], lane, wsc + cl * U_WPITCH, pk + cl * U_PPITCH, n_s, win_s, &winv[cl]);
+      else if (lane == 0)
+        winv[cl] = 1.f;
     }
   }
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+#ifdef SINC_ABLATION
+  dbg_c1 = clock64();
+#endif
   const uint32_t tmem = *tmem_slot;
 
-  // W' -> TMEM: lane = row m = 8*cl + r, column = tap pair (s, s+1), W'[m, s] = w[cl, s - r]
-  // (two warps per TMEM lane quarter, alternate 16-tap column groups)
+  // W' -> TMEM: lane = row m = 8*cl + r, column = tap pair (s, s+1), W'[m, s] = w[cl, s - r]: eight consecutive words of the
+  // copy whose alignment matches the parity of r (two warps per TMEM lane quarter, alternate 16-tap column groups)
   if (warp < 8) {
     const int m = tid & 127, cl = m >> 3, r = m & 7;
     const uint32_t base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    const float* wr = wsc + cl * U_WPITCH;
+    const uint32_t* pr = pk + cl * U_PPITCH + ((r & 1) ? U_P_ODD + (9 - r) / 2 : (8 - r) / 2);
+#pragma unroll 1
     for (int s0 = 16 * (warp >> 2); s0 < U_KS; s0 += 32) {
       uint32_t hi[8], lo[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const int k0 = s0 + 2 * e - r, k1 = k0 + 1;
-        uint16_t h0, l0, h1, l1;
-        u_split_f16((k0 >= 0 && k0 < K) ? wr[k0] : 0.f, h0, l0);
-        u_split_f16((k1 >= 0 && k1 < K) ? wr[k1] : 0.f, h1, l1);
-        hi[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        lo[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        hi[e] = pr[s0 / 2 + e];
+        lo[e] = pr[U_P_LO + s0 / 2 + e];
       }
       tc::tmem_st8(base + U_TM_WHI + s0 / 2, hi);
       tc::tmem_st8(base + U_TM_WLO + s0 / 2, lo);
@@ -226,6 +275,11 @@ __global__ void __launch_bounds__(U_THREADS, 1) fwd_tc16_kernel(const FwdTc16Arg
   tc::fence_before_sync();
   __syncthreads();  // the setup scratch becomes staging buffer 0
   tc::fence_after_sync();
+#ifdef SINC_ABLATION
+  dbg_c2 = clock64();
+  if (FABL(5) && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77))
+    printf("fwd prologue cta %d: zero+synth %lld cycles, W' build %lld cycles\n", (int)blockIdx.x, dbg_c1 - dbg_c0, dbg_c2 - dbg_c1);
+#endif
 
   const int64_t my_tiles = slot < a.ntiles ? (a.ntiles - slot + per_blk - 1) / per_blk : 0;
   bool ok = true;

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 PLANS = {
-    "fw": ("SINC_ABLATE_FW", {0: "full", 16: "full, round-1 prologue (one filter per warp, two rounds)", 1: "epilogue idle (stores of stale staging)", 2: "no stores to y", 3: "epilogue idle + no stores",
+    "fw": ("SINC_ABLATE_FW", {0: "full", 1: "epilogue idle (stores of stale staging)", 2: "no stores to y", 3: "epilogue idle + no stores",
                               4: "no MMAs", 8: "producers idle", 12: "no MMAs, producers idle (stores only)",
                               15: "barriers only"}),
     "bi": ("SINC_ABLATE_BI", {0: "full", 32: "full, boxes from L2 (perfect feed)", 3: "epilogue idle", 12: "producers idle (TMA boxes still arrive)",
