@@ -57,6 +57,8 @@ __device__ __forceinline__ void finalize_chain_rule(const Bank& bank, const Chan
                                                     double* scratch, float* grad_low, float* grad_band) {
   const int K = bank.K, H = (K - 1) / 2;
   const int tid = threadIdx.x;
+  // the two parameters whose signs close the chain rule: loaded now, used by thread 0 at the very end
+  const float p_low = tid == 0 ? bank.low_hz[c] : 0.f, p_band = tid == 0 ? bank.band_hz[c] : 0.f;
   double sabs = 0.0, dot = 0.0;
   for (int k = tid; k < K; k += NT) {
     sabs += fabs(us[k]);
@@ -85,8 +87,8 @@ __device__ __forceinline__ void finalize_chain_rule(const Bank& bank, const Chan
     const double d_high = d_fhi / bank.sr;
     const double d_low_direct = d_flo / bank.sr;
     const double un = cc.unclamped ? 1.0 : 0.0;
-    grad_band[c] = (float)(un * d_high * sgn((double)bank.band_hz[c]));
-    grad_low[c] = (float)((d_low_direct + un * d_high) * sgn((double)bank.low_hz[c]));
+    grad_band[c] = (float)(un * d_high * sgn((double)p_band));
+    grad_low[c] = (float)((d_low_direct + un * d_high) * sgn((double)p_low));
   }
 }
 

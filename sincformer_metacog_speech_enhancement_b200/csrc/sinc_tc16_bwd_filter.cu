@@ -73,8 +73,8 @@ constexpr int F2_GSTAGE_BYTES = 64 * F2_GPITCH;
 constexpr int F2_SM_G = 0;                  // [F2_GSTAGES][64 rows][F2_GPITCH]
 constexpr int F2_SM_X = F2_SM_G + F2_GSTAGES * F2_GSTAGE_BYTES;  // [buf 2][rho 4][hi/mid 2][F2_XLEN] bf16
 constexpr int F2_SM_BAR = F2_SM_X + 2 * 8 * F2_XLEN * 2;
-constexpr int F2_SM_FIN = F2_SM_BAR + 512;  // fused finalize (doubles): us[256] chi[256] clo[256] Gs[256] part[2][256] scratch[64]
-constexpr int F2_SM_TOTAL = F2_SM_FIN + (6 * 256 + 64) * 8;
+constexpr int F2_SM_FIN = F2_SM_BAR + 512;  // fused finalize (doubles): us[256] chi[256] clo[256] Gs[256] part[2][256] scratch[64] ChanCoef
+constexpr int F2_SM_TOTAL = F2_SM_FIN + (6 * 256 + 64 + 4) * 8;   // + the filter's ChanCoef
 static_assert(28 + F2_GSTAGES <= 32, "barrier table: tmem_slot lives at bars + 32");
 static_assert((F2_XLEN * 2) % 16 == 0, "waveform copies must stay 16-byte aligned");
 
@@ -524,8 +524,11 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
           reinterpret_cast<uint32_t*>(a.tab)[i] = tab_header_word(a.bank, i);
       for (int c = 4 * blockIdx.x + (warp - 12); c < 64; c += 4 * gridDim.x) tab_write_row(a.bank, a.tab, c, lane);
     }
-    if (a.fin_sync && (int)blockIdx.x < C)  // the G-independent factors of this CTA's filter (read in the tail, below)
-      finalize_factors(a.bank, chan_coef(a.bank, blockIdx.x), tid - 384, 128, fin_us, fin_us + 256, fin_us + 512);
+    if (a.fin_sync && (int)blockIdx.x < C) {  // the G-independent factors of this CTA's filter (read in the tail, below)
+      const ChanCoef cc = chan_coef(a.bank, blockIdx.x);
+      if (tid == 384) *reinterpret_cast<ChanCoef*>(fin_us + 6 * 256 + 64) = cc;
+      finalize_factors(a.bank, cc, tid - 384, 128, fin_us, fin_us + 256, fin_us + 512);
+    }
     const int quarter = warp & 3;
     const int m = 32 * quarter + lane;
     const uint32_t lane_base = (uint32_t)(32 * quarter) << 16;
@@ -629,8 +632,11 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
     const int K = a.K, slots = gridDim.x;
     uint32_t fin_parity = 0;
     for (int c = blockIdx.x; c < C; c += gridDim.x) {
-      const ChanCoef cc = chan_coef(a.bank, c);
+      // the filter's scalars were computed next to its factors at the start of the kernel (parameter loads and an fp64
+      // division are ~1.5k cycles of latency that would sit on the critical path here)
+      ChanCoef cc = *reinterpret_cast<const ChanCoef*>(fin_us + 6 * 256 + 64);
       if (c != (int)blockIdx.x) {   // grids smaller than the filter count: later filters get their factors here
+        cc = chan_coef(a.bank, c);
         __syncthreads();
         if (tid >= 384) finalize_factors(a.bank, cc, tid - 384, 128, us, chi, clo);
       }
@@ -650,7 +656,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) bwd_filter_tc16_kernel(const Bw
         // may complete before thread 0 has posted the byte count: the transaction count of an mbarrier may run negative.
         if (tid == 0) tc::mbar_expect_tx(fin_bar, (uint32_t)slots * 1024u);
         if (tc::elect_one()) {
-          asm volatile("fence.proxy.async;" ::: "memory");
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           const uint32_t bar = tc::smem_addr(fin_bar);
           for (int sl = warp; sl < slots; sl += F2_THREADS / 32)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

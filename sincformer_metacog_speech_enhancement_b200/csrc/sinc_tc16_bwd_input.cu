@@ -40,6 +40,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <type_traits>
@@ -167,6 +168,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   __syncthreads();
   tc::griddep_wait();     // everything above touched shared memory, TMEM and the (parameter-space) tensor map only
   tc::griddep_launch();
+#ifdef SINC_ABLATION
+  const long long dbg_c0 = clock64();
+  long long dbg_c1 = 0;
+#endif
   {
     float* wst = reinterpret_cast<float*>(ring);  // fp32 filters [c][256], rows >= C and taps >= K stay zero
     // The filters come from the table the grad-filter kernel left in the workspace when that table provably belongs
@@ -175,19 +180,45 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
     if (a.tab) {
       int good = tab_shape_ok(a.bank) ? 1 : 0;
       if (good) {
+        // Every load of this block is issued before the first use (the table rows, the row checksums, the header words and
+        // the parameters they are compared with): ONE L2 round trip.  As a loop over rows this was four dependent round
+        // trips and 10k cycles, on the critical path of every CTA.
+        static_assert(H2_THREADS / 32 == 16, "four table rows per warp");
         const uint32_t* hdr = reinterpret_cast<const uint32_t*>(a.tab);
-        for (int i = tid; i < kTabHdrWords; i += H2_THREADS) good &= (hdr[i] == tab_header_word(a.bank, i)) ? 1 : 0;
         const float4* src = reinterpret_cast<const float4*>(a.tab + kTabDataOff);
         const unsigned long long* rowsum = reinterpret_cast<const unsigned long long*>(a.tab + kTabRowsumOff);
-        for (int c = warp; c < 64; c += H2_THREADS / 32) {
+        float4 v[4][2];
+        unsigned long long rs[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = warp + 16 * i;
+          v[i][0] = src[c * 64 + lane];
+          v[i][1] = src[c * 64 + lane + 32];
+          rs[i] = rowsum[c];
+        }
+        uint32_t hw[2] = {0u, 0u}, bw[2] = {0u, 0u};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int w = tid + i * H2_THREADS;
+          if (w < kTabHdrWords) {
+            hw[i] = hdr[w];
+            bw[i] = tab_header_word(a.bank, w);
+          }
+        }
+        static_assert(kTabHdrWords <= 2 * H2_THREADS, "two header words per thread");
+        good &= (hw[0] == bw[0] && hw[1] == bw[1]) ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = warp + 16 * i;
           unsigned long long sum = 0ull;
 #pragma unroll
-          for (int q = lane; q < 64; q += 32) {
-            const float4 v = src[c * 64 + q];
-            reinterpret_cast<float4*>(wst)[c * 64 + q] = v;
-            sum += tab_mix(v.x, 4 * q) + tab_mix(v.y, 4 * q + 1) + tab_mix(v.z, 4 * q + 2) + tab_mix(v.w, 4 * q + 3);
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int q = lane + 32 * h2;
+            const float4 f = v[i][h2];
+            reinterpret_cast<float4*>(wst)[c * 64 + q] = f;
+            sum += tab_mix(f.x, 4 * q) + tab_mix(f.y, 4 * q + 1) + tab_mix(f.z, 4 * q + 2) + tab_mix(f.w, 4 * q + 3);
           }
-          good &= (warp_sum_u64(sum) == rowsum[c]) ? 1 : 0;
+          good &= (warp_sum_u64(sum) == rs[i]) ? 1 : 0;
         }
       }
       tab_ok = __syncthreads_and(good) != 0;
@@ -205,19 +236,22 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
+#ifdef SINC_ABLATION
+  dbg_c1 = clock64();
+#endif
   const uint32_t tmem = *tmem_slot;
   // TMEM map: [0,384) THREE accumulators of 128 columns; [384,448) W' hi, [448,512) W' mid (column = e*32 + c/2).
   // Three, not two: the accumulator of stage s is free again when the epilogue has read it out of TMEM, which takes
   // longer than the MMAs of one stage (a barrier wake-up on each side of 64 KB of tcgen05.ld); with two buffers the
   // issuer waited for that every stage (r02e: 2500 cycles per stage against 1536 of MMAs).
-  if (warp < 4) {
+  {   // all 16 warps: four per TMEM lane quarter, two of the eight (tap parity, 16-filter group) column blocks each
     const float* wst = reinterpret_cast<const float*>(ring);
-    const int kp = 32 * warp + lane;  // tap pair = TMEM lane
-    const uint32_t lane_base = (uint32_t)(32 * warp) << 16;
+    const int kp = 32 * (warp & 3) + lane;  // tap pair = TMEM lane
+    const uint32_t lane_base = (uint32_t)(32 * (warp & 3)) << 16;
 #pragma unroll 1
-    for (int e = 0; e < 2; ++e) {
-#pragma unroll 1
-      for (int cg = 0; cg < 4; ++cg) {
+    for (int blk = warp >> 2; blk < 8; blk += 4) {
+      const int e = blk >> 2, cg = blk & 3;
+      {
         uint32_t hi[8], mid[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -237,6 +271,10 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
   tc::fence_before_sync();
   __syncthreads();  // the filter staging area becomes the B ring
   tc::fence_after_sync();
+#ifdef SINC_ABLATION
+  if (ABL(6) && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 100))
+    printf("bi prologue cta %d: table %lld cycles, W' build %lld cycles\n", (int)blockIdx.x, dbg_c1 - dbg_c0, clock64() - dbg_c1);
+#endif
 
   // ---------------- work: a contiguous range of 128-sample output blocks, cut into per-utterance runs ----------
   // Every role walks the same sequence of (run, stage) pairs.  The three roles are separate top-level branches
