@@ -14,6 +14,7 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
                  `frac_of_raw_bf16` against the measured bf16 dense rate itself
   kernels        all three kernels
   sustained      the same step, >= 2000 back to back (the SM clock settles lower than in the short burst)
+  cuda_graph     the same step captured once in a CUDA graph and replayed (N = 1): the launch-bound small workloads
   gpu_reference  the reference's own torch ops (synthesis + F.conv1d, autograd backward) through cuDNN on this GPU,
                  TF32 on and off -- the practical GPU bar
   cfg4 / cfg5    BASELINE configs 4 and 5 as specified: global 1024 x 48 000 fp32 resp. 64 x 960 000 bf16, rows
@@ -674,6 +675,26 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": Bs * T / SR_AUDIO / min(ts), "unit": "audio-s/s",
                                     "cores": torch.get_num_threads(), "kind": kind,
                                     "sample": f"reference CPU torch path ({kind}), B={Bs} x T={T} fwd+bwd, best of 3"}
+    # --- the same step captured in a CUDA graph and replayed (N = 1): what is left when the host side of the three launches
+    #     is gone -- matters for the launch-bound small workloads (cfg 1), not for cfg 2.  Last, so that a failed capture
+    #     cannot disturb another measurement.
+    if world == 1 and not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    step_resident()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_resident()
+            ms_g = timed(graph.replay, max(args.steps, 20), 3) / max(args.steps, 20)
+            line["cuda_graph"] = {"ms_per_step": ms_g, "value": audio_per_step / (ms_g * 1e-3), "unit": "audio-s/s",
+                                  "note": "module forward + backward captured once with torch.cuda.graph, replayed"}
+        except Exception as e:
+            line["cuda_graph"] = {"unavailable": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -692,6 +713,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-gpu-ref", action="store_true", help="skip the torch/cuDNN gpu_reference leg")
     ap.add_argument("--no-sub", action="store_true", help="skip the cfg4 / cfg5 strong-scaling sub-records")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay record")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
