@@ -207,7 +207,7 @@ int sinc_backward(const sinc_filterbank* fb, const float* x, int64_t x_stride_b,
     const int esz = gy_dtype == SINC_DTYPE_F32 ? 4 : 2;
     const bool rows_aligned = T % (16 / esz) == 0 && reinterpret_cast<uintptr_t>(grad_y) % 16 == 0;
     const bool tc_wanted = o.engine == SINC_ENGINE_AUTO || o.engine == SINC_ENGINE_TC;
-    if (!rows_aligned && tc_wanted && bank.K <= 256 && (grad_x == nullptr || bank.C <= 64) && T % 8 != 0) {
+    if (!rows_aligned && tc_wanted && bank.K <= 256 && T % 8 != 0) {
       const RepitchLayout rl = repitch_layout(B, T, bank.C, bank.K);
       if (workspace && workspace_bytes >= rl.total_bytes) {
         uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace) + 255) / 256 * 256);

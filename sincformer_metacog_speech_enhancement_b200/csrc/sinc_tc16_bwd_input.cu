@@ -94,6 +94,10 @@ struct BwdInputTc16Args {
   int64_t nblocks;         // B * blocks_per_row
   long long* phase;        // diagnostic time stamps (CTA 0), may be null
   const uint8_t* tab;      // filter table left in the workspace by the grad-filter kernel (sinc_synth.cuh), or nullptr
+  // More than 64 filters: one launch per block of 64 (`bank`, `g` and the tensor map describe the block), every launch
+  // after the first adds to gx.  c_total = filter rows per utterance in grad_y (the batch stride).
+  int c_total;
+  int accumulate;
 #ifdef SINC_ABLATION
   int ablate;              // ablation build only (tools/ablate.py): bit 0 epilogue skips col2im, 1 epilogue skips the TMEM
                            // load too, 2 producers skip conversion + plane stores, 3 producers skip the staging reads too,
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
       (void)s_out; (void)e_out;
       using gvec = typename std::conditional<GB, uint2, float4>::type;   // 4 consecutive positions of one filter row
       constexpr int ESZ = GB ? 2 : 4;
-      const uint8_t* gb = reinterpret_cast<const uint8_t*>(a.g) + (b * C) * T * ESZ;
+      const uint8_t* gb = reinterpret_cast<const uint8_t*>(a.g) + (b * a.c_total) * T * ESZ;
       gvec vv[16];
       auto issue_box = [&](int i, uint32_t q) {  // stage i of this run -> box q % H2_NBOX (the whole warp calls; one lane issues)
         if (tc::elect_one()) {
@@ -508,7 +512,7 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
             }
             if (o < H2_NS) {
               const int64_t t = col0 - H + o;
-              if (t >= s_out && t < e_out) a.gx[b * T + t] = acc;
+              if (t >= s_out && t < e_out) a.gx[b * T + t] = a.accumulate ? a.gx[b * T + t] + acc : acc;
             } else {
               cout[o - H2_NS] = acc;
             }
@@ -646,7 +650,8 @@ __global__ void __launch_bounds__(H2_THREADS, 1)
 bool tc16_bwd_input_supported(int C, int K, int64_t T, const void* g, int g_dtype, const DeviceInfo& di) {
   // (the rows of the TMA tensor map must be 16-byte aligned: T % 4 for fp32, T % 8 for bf16 grad_y)
   const bool rows_ok = g_dtype == SINC_DTYPE_F32 ? T % 4 == 0 : (g_dtype == SINC_DTYPE_BF16 && T % 8 == 0);
-  return C <= 64 && K <= 256 && rows_ok &&
+  (void)C;  // any filter count: blocks of 64 filters, one launch each (launch_bwd_input_tc16)
+  return K <= 256 && rows_ok &&
          reinterpret_cast<uintptr_t>(g) % 16 == 0 && di.max_smem_optin >= H2_SM_TOTAL + 1024;
 }
 
@@ -668,12 +673,13 @@ EncodeTiledFn encode_tiled_fn() {
 }
 // grad_y [B][C][T] as a 3-D tensor (T fastest); box = 32 positions x 64 filters of one utterance, swizzle = the
 // row length of the box (128 bytes fp32, 64 bytes bf16)
-bool make_grad_map(CUtensorMap* m, const void* g, bool bf16, int64_t B, int C, int64_t T) {
+// (C rows of the block starting at g; c_total rows per utterance)
+bool make_grad_map(CUtensorMap* m, const void* g, bool bf16, int64_t B, int C, int c_total, int64_t T) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   const cuuint64_t esz = bf16 ? 2 : 4;
   const cuuint64_t dims[3] = {(cuuint64_t)T, (cuuint64_t)C, (cuuint64_t)B};
-  const cuuint64_t strides[2] = {(cuuint64_t)T * esz, (cuuint64_t)T * esz * (cuuint64_t)C};
+  const cuuint64_t strides[2] = {(cuuint64_t)T * esz, (cuuint64_t)T * esz * (cuuint64_t)c_total};
   const cuuint32_t box[3] = {32, 64, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(g), dims,
@@ -686,32 +692,42 @@ bool make_grad_map(CUtensorMap* m, const void* g, bool bf16, int64_t B, int C, i
 cudaError_t launch_bwd_input_tc16(const Bank& bank, const void* gy, int gy_dtype, float* gx, int64_t B, int64_t T,
                                   const DeviceInfo& di, cudaStream_t st, const uint8_t* filter_table, int reserved_sms,
                                   long long* phase) {
-  BwdInputTc16Args a;
-  a.bank = bank;
-  a.g = gy;
-  a.gx = gx;
-  a.B = B;
-  a.T = T;
-  a.blocks_per_row = ceil_div64(T, H2_NS);
-  a.nblocks = B * a.blocks_per_row;
-  a.phase = phase ? phase + 6 : nullptr;  // sinc_options.phase_stamps (diagnostic, normally null)
-  a.tab = filter_table;
-#ifdef SINC_ABLATION
-  a.ablate = getenv("SINC_ABLATE_BI") ? atoi(getenv("SINC_ABLATE_BI")) : 0;
-#endif
   int sms = di.sm_count - reserved_sms;  // data-parallel: a few SMs stay free for the all-reduce in flight
   if (sms < 1) sms = 1;
-  const int grid = (int)(a.nblocks < sms ? a.nblocks : sms);
   const size_t smem = H2_SM_TOTAL + 1024;
   auto kern = gy_dtype == SINC_DTYPE_BF16 ? bwd_input_tc16_kernel<true> : bwd_input_tc16_kernel<false>;
   cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)smem);
   if (e != cudaSuccess) return e;
-  CUtensorMap gmap;
-  memset(&gmap, 0, sizeof(gmap));
-  if (!make_grad_map(&gmap, gy, gy_dtype == SINC_DTYPE_BF16, B, bank.C, T)) return cudaErrorNotSupported;
-  e = launch_pdl(kern, grid, H2_THREADS, smem, st, a, gmap);
-  if (e != cudaSuccess) return e;
-  count_launch();
+  const size_t esz = gy_dtype == SINC_DTYPE_BF16 ? 2 : 4;
+  // the GEMM's K dimension holds 64 filters (x 2 tap parities): wider banks take one launch per block of 64 filters,
+  // each adding its share to gx (every output sample is written by exactly one CTA per launch: no race)
+  for (int cb0 = 0; cb0 < bank.C; cb0 += 64) {
+    BwdInputTc16Args a;
+    a.bank = bank;
+    a.bank.low_hz = bank.low_hz + cb0;
+    a.bank.band_hz = bank.band_hz + cb0;
+    a.bank.C = bank.C - cb0 < 64 ? bank.C - cb0 : 64;
+    a.g = reinterpret_cast<const uint8_t*>(gy) + (size_t)cb0 * (size_t)T * esz;
+    a.c_total = bank.C;
+    a.accumulate = cb0 > 0 ? 1 : 0;
+    a.gx = gx;
+    a.B = B;
+    a.T = T;
+    a.blocks_per_row = ceil_div64(T, H2_NS);
+    a.nblocks = B * a.blocks_per_row;
+    a.phase = phase ? phase + 6 : nullptr;  // sinc_options.phase_stamps (diagnostic, normally null)
+    a.tab = bank.C <= 64 ? filter_table : nullptr;   // the table holds one block of 64 filters
+#ifdef SINC_ABLATION
+    a.ablate = getenv("SINC_ABLATE_BI") ? atoi(getenv("SINC_ABLATE_BI")) : 0;
+#endif
+    const int grid = (int)(a.nblocks < sms ? a.nblocks : sms);
+    CUtensorMap gmap;
+    memset(&gmap, 0, sizeof(gmap));
+    if (!make_grad_map(&gmap, a.g, gy_dtype == SINC_DTYPE_BF16, B, a.bank.C, bank.C, T)) return cudaErrorNotSupported;
+    e = launch_pdl(kern, grid, H2_THREADS, smem, st, a, gmap);
+    if (e != cudaSuccess) return e;
+    count_launch();
+  }
   return cudaGetLastError();
 }
 

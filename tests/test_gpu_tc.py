@@ -143,6 +143,8 @@ TC_BWD_SHAPES = [
     (64, 251, 8000, 2, 4),
     (64, 251, 16000, 40, 2048),     # several tiles per CTA slot
     (64, 251, 16000, 24, 32768),    # > 8 tiles per CTA: two accumulation windows (double-buffered flush) in grad-filter
+    (96, 251, 16000, 3, 4096),      # more than 64 filters: grad-input in two launches (blocks of 64), the second adds to gx
+    (130, 129, 8000, 2, 3001),      # three blocks (64 + 64 + 2), ragged length on top
     (8, 250, 8000, 2, 2048),
     (70, 31, 44100, 2, 776),
     (130, 9, 8000, 1, 600),
@@ -166,11 +168,11 @@ def test_tc_backward_vs_oracle(engine, C, K, sr, B, T):
     out = run_dut(dut, x, g, bwd_engine=engine)
     eng = out["engines"]
     # ragged lengths: under "tc" the backward re-pitches grad_y once and stays on the 16-bit kernels (needs both passes
-    # to fit: K <= 256, C <= 64 for grad-input); under "tc_tf32" only grad-input takes any length
-    ragged16 = engine == "tc" and T % 4 != 0 and K <= 256 and C <= 64
+    # to fit: K <= 256); under "tc_tf32" only grad-input takes any length
+    ragged16 = engine == "tc" and T % 4 != 0 and K <= 256
     if (T % 4 == 0 or ragged16) and K <= (256 if engine == "tc" else 312):
         assert eng["bwd_filter"] == ("tc16" if engine == "tc" else "tc_tf32"), eng
-    if C <= 64 and K <= 256:
+    if K <= 256 and (C <= 64 or engine == "tc"):   # the 16-bit grad-input takes any filter count (blocks of 64), 3xTF32 up to 64
         assert eng["bwd_input"] == ("tc16" if engine == "tc" and (T % 4 == 0 or ragged16) else "tc_tf32"), eng
     check_against(orc, out, x, g)
 
