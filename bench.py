@@ -14,7 +14,9 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
                  `frac_of_raw_bf16` against the measured bf16 dense rate itself
   kernels        all three kernels
   sustained      the same step, >= 2000 back to back (the SM clock settles lower than in the short burst)
-  cuda_graph     the same step captured once in a CUDA graph and replayed (N = 1): the launch-bound small workloads
+  launch / eager the headline step is captured once in a CUDA graph (module forward + backward, the all-reduce included)
+                 and replayed -- at N = 8 the host side of an eager step (0.5 ms) is slower than the GPU; `eager` = the
+                 same K steps launched through the module API
   gpu_reference  the reference's own torch ops (synthesis + F.conv1d, autograd backward) through cuDNN on this GPU,
                  TF32 on and off -- the practical GPU bar
   cfg4 / cfg5    BASELINE configs 4 and 5 as specified: global 1024 x 48 000 fp32 resp. 64 x 960 000 bf16, rows
@@ -345,11 +347,47 @@ def run_ours(args):
         except Exception:
             return None
 
+    # --- how the step is launched.  Through the module API a step costs ~0.2 ms of HOST time (Python, autograd, ctypes; at
+    #     N = 8 with the in-backward all-reduce 0.48-0.53 ms per step on the slowest rank: eight ranks share the box's host
+    #     cores -- tools/n8_steps.py), i.e. the host, not the GPU, paces a multi-rank run.  The step is therefore captured
+    #     ONCE in a CUDA graph (module forward + backward, the NCCL all-reduce included) and replayed: the same kernels in
+    #     the same order, one graph launch per step.  Every rank must agree (the capture contains a collective): if the
+    #     capture fails anywhere, all ranks run eagerly.  The eager figure is reported next to it (`eager`).
+    def capture_step(fn):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        torch.cuda.synchronize()
+        return graph
+
+    n0 = sb.kernel_launch_count()
+    step_resident()
+    torch.cuda.synchronize()
+    launches = sb.kernel_launch_count() - n0
+    step_fn, launch_mode, graph = step_resident, "eager", None
+    if not args.no_graph and not os.environ.get("SINC_BENCH_NO_GRAPH"):
+        ok_here = 1.0
+        try:
+            graph = capture_step(step_resident)
+        except Exception as e:       # noqa: BLE001 -- any failure means "eager", on every rank
+            sys.stderr.write(f"[bench] CUDA-graph capture failed on rank {rank}: {e!r}\n")
+            ok_here = 0.0
+        flag = torch.tensor([ok_here], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) > 0.5:
+            step_fn, launch_mode = graph.replay, "cuda_graph"
+
     # --- headline: whole step, inputs resident in HBM --------------------------------------------------
     with ClockSampler(local) as clk:
-        n0 = sb.kernel_launch_count()
-        ms_total = timed(step_resident, args.steps, args.warmup)
-        launches = (sb.kernel_launch_count() - n0) * args.steps // (args.steps + args.warmup)
+        ms_total = timed(step_fn, args.steps, args.warmup)
         real = in_kernel_clocks(m, step_resident)
     clocks = clk.summary()
     if real:
@@ -522,9 +560,92 @@ def run_ours(args):
             ms = float(t.item())
         return ms
 
+    # The same pipeline as two CUDA graphs (even / odd step), when the headline step could be captured: graph k holds, as
+    # three parallel branches, the H2D copy of step k+1's waveforms, step k itself (module forward + backward, all-reduce
+    # included; its results go to a static device buffer) and the D2H read-back of step k-1's results.  The eager loop
+    # above costs ~0.35 ms of host time per step (events, streams, autograd, ctypes) -- with several ranks on one box the
+    # host, not the link or the GPU, set its pace (N = 2: 0.45 - 0.96 ms from run to run).
+    e2e_mode = "eager"
+    if launch_mode == "cuda_graph":
+        ok_here = 1.0
+        try:
+            res_gx = [torch.zeros(B, 1, T, device=dev) for _ in range(2)] if need_x else None
+            res_gp = [torch.zeros(2, C, 1, device=dev) for _ in range(2)]
+
+            def e2e_body(slot):
+                main = torch.cuda.current_stream(dev)
+                h2d_stream.wait_stream(main)
+                d2h_stream.wait_stream(main)
+                with torch.cuda.stream(h2d_stream):                      # branch 1: the next step's waveforms
+                    xdev[slot ^ 1].copy_(x_host, non_blocking=True)
+                with torch.cuda.stream(d2h_stream):                      # branch 2: the previous step's results
+                    if need_x:
+                        gx_host.copy_(res_gx[slot ^ 1], non_blocking=True)
+                    gp_host.copy_(res_gp[slot ^ 1], non_blocking=True)
+                xd = xdev[slot].requires_grad_(need_x)                   # branch 3: this step
+                m.low_hz_.grad = None
+                m.band_hz_.grad = None
+                m(xd).backward(g)
+                if need_x:
+                    res_gx[slot].copy_(xd.grad)
+                res_gp[slot][0].copy_(m.low_hz_.grad)
+                res_gp[slot][1].copy_(m.band_hz_.grad)
+                xdev[slot].requires_grad_(False)
+                xdev[slot].grad = None
+                main.wait_stream(h2d_stream)
+                main.wait_stream(d2h_stream)
+
+            xdev[0].copy_(x_host)
+            xdev[1].copy_(x_host)
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for sl in (0, 1, 0, 1):
+                    e2e_body(sl)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize()
+            e2e_graphs = []
+            for sl in (0, 1):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    e2e_body(sl)
+                e2e_graphs.append(gr)
+            torch.cuda.synchronize()
+        except Exception as e:       # noqa: BLE001
+            sys.stderr.write(f"[bench] e2e graph capture failed on rank {rank}: {e!r}\n")
+            ok_here = 0.0
+        flag = torch.tensor([ok_here], device=dev)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) > 0.5:
+            e2e_mode = "cuda_graph"
+            gstate = {"k": 0}
+
+            def step_e2e_graph():
+                e2e_graphs[gstate["k"] & 1].replay()
+                gstate["k"] += 1
+
+            def timed_e2e(steps, warmup):   # noqa: F811 -- same contract as the eager version above
+                for _ in range(warmup + (warmup & 1)):
+                    step_e2e_graph()
+                sync_all()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(steps):
+                    step_e2e_graph()
+                e1.record()              # every graph joins its copy branches: the last copies are inside the region
+                sync_all()
+                ms = e0.elapsed_time(e1)
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t.item())
+                return ms
+
     # Three runs of exactly K steps each, the MEDIAN reported (all three listed): a timed region of K x 0.4 ms is short
     # enough for a single host-side hiccup (a few ms on some boxes for 12 MB of pinned copies) to move its mean by 30 %.
-    e2e_runs = [timed_e2e(args.steps, args.warmup if i == 0 else 1) / args.steps for i in range(3)]
+    e2e_runs = [timed_e2e(args.steps, args.warmup if i == 0 else 2) / args.steps for i in range(3)]
     ms_e2e = sorted(e2e_runs)[1]
     e2e_value = world * audio_per_step / (ms_e2e * 1e-3)
 
@@ -553,18 +674,23 @@ def run_ours(args):
         "engine": args.engine,
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "ms_per_step": ms_e2e, "ms_per_step_runs": e2e_runs,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_link": link,
+                "launch": e2e_mode,
                 "note": "nn.Module API; every step copies its waveforms from pinned host memory and reads grad-input + parameter "
                         "grads back to pinned host memory (one copy stream per direction, double-buffered: copies overlap the "
                         "neighbouring steps' compute); grad_y resident (produced on-device by the next layer); median of three runs "
                         "of K steps each (ms_per_step_runs)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * args.steps,
+        "launch": launch_mode,
         "clocks": clocks,
     }
     line.update(extra)
+    if launch_mode == "cuda_graph":     # the same K steps launched eagerly through the module API
+        ms_eager = timed(step_resident, args.steps, 3) / args.steps
+        line["eager"] = {"ms_per_step": ms_eager, "value": world * audio_per_step / (ms_eager * 1e-3), "unit": "audio-s/s"}
 
     # --- sustained: the same step >= 2000 times back to back (the SM clock settles under tensor + HBM load) ---------
     if args.sustained > 0:
-        ms_sus = timed(step_resident, args.sustained, 3) / args.sustained
+        ms_sus = timed(step_fn, args.sustained, 3) / args.sustained
         rec = {"steps": args.sustained, "ms_per_step": ms_sus, "value": world * audio_per_step / (ms_sus * 1e-3),
                "unit": "audio-s/s", "vs_burst": ms_step / ms_sus}
         real = in_kernel_clocks(m, step_resident)
@@ -675,30 +801,32 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": Bs * T / SR_AUDIO / min(ts), "unit": "audio-s/s",
                                     "cores": torch.get_num_threads(), "kind": kind,
                                     "sample": f"reference CPU torch path ({kind}), B={Bs} x T={T} fwd+bwd, best of 3"}
-    # --- the same step captured in a CUDA graph and replayed (N = 1): what is left when the host side of the three launches
-    #     is gone -- matters for the launch-bound small workloads (cfg 1), not for cfg 2.  Last, so that a failed capture
-    #     cannot disturb another measurement.
-    if world == 1 and not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    step_resident()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step_resident()
-            ms_g = timed(graph.replay, max(args.steps, 20), 3) / max(args.steps, 20)
-            line["cuda_graph"] = {"ms_per_step": ms_g, "value": audio_per_step / (ms_g * 1e-3), "unit": "audio-s/s",
-                                  "note": "module forward + backward captured once with torch.cuda.graph, replayed"}
-        except Exception as e:
-            line["cuda_graph"] = {"unavailable": repr(e)[:200]}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    # Teardown.  A CUDA graph that holds NCCL kernels must be gone before its process group is; and whatever happens after the
+    # line is out must not keep the process alive (a captured collective made destroy_process_group hang once, r06): a
+    # watchdog ends the process with status 0 if the orderly teardown has not finished within 20 s.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    import threading
+    dog = threading.Timer(20.0, lambda: os._exit(0))
+    dog.daemon = True
+    dog.start()
+    step_fn = None
+    if graph is not None:
+        graph.reset()
+        del graph
+    if e2e_mode == "cuda_graph":
+        for gr in e2e_graphs:
+            gr.reset()
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        if launch_mode == "cuda_graph":
+            os._exit(0)      # every rank is past the barrier and has nothing left to say: skip NCCL's teardown altogether
         dist.destroy_process_group()
+    dog.cancel()
 
 
 def main():
