@@ -1,7 +1,9 @@
 // tcgen05 engine, grad-filter, 16-bit split operands:
 //     G[c,k] = sum_b sum_t g[b,c,t] x[b,t+k-H]                          (ConvolutionBackward0, grad-weight)
 // bf16 hi/mid split (three kind::f16 MMAs per product, fp32 accumulate), sm_100a only.
-// Output: partial tiles for finalize_kernel (layout 2).
+// Output: one partial tile per CTA (layout 2 of sinc_finalize.cuh); for one filter block (C <= 64) the kernel reduces the
+// tiles and applies the synthesis chain rule in its own tail (see "fused finalize" at the end of the kernel), otherwise
+// finalize_kernel does.
 //
 // Precision: 16 significant bits per operand, ~5e-6 max-norm relative on G against the fp64 oracle (gate 1e-4);
 // the 3xTF32 kernel (sinc_tc_bwd_filter.cu) stays available as SINC_ENGINE_TC_TF32.
@@ -17,11 +19,13 @@
 // and 4..7), so four shifts x N = 32 columns cover K <= 256 taps with no redundant MMA work (the 3xTF32 kernel
 // computes every tap in both interleaves: 78 % useful).  Each g sample is converted twice (once per interleave).
 //
-// A (= grad_y) is staged as raw fp32 rows by 1-D bulk copies (4 stages x 64 rows x 128 samples in flight), read back
-// row-per-lane, split into bf16 hi/mid and written with tcgen05.st into a TMEM ring of 4 slots x 2 K-steps (one
+// A (= grad_y) is staged as raw fp32 rows by 1-D bulk copies (2 stages x 64 rows x 256 samples = 128 KB in flight: 1 KB
+// per copy -- 512-byte copies are capped at 5.2 TB/s by the issue rate of cp.async.bulk), read back row-per-lane, split
+// into bf16 hi and NEGATED mid (tc::split_bf16x2_negmid: four instructions per pair; the MMA that consumes the mid piece
+// negates A in its instruction descriptor) and written with tcgen05.st into a TMEM ring of 4 slots x 4 K-steps (one
 // producer/issuer handshake per slot); every MMA is the TS form (A from TMEM), the B tiles are 1 KB each.
-//     TMEM  two accumulator sets [0,128) / [128,256): D_rho = 32 columns  |  A ring [256,384): 16 columns per K-step
-//     SMEM  grad_y staging ring 136 KB  |  2 x 4 x (hi,mid) shifted waveform tiles, 25 KB
+//     TMEM  two accumulator sets [0,128) / [128,256): D_rho = 32 columns  |  A ring [256,512): 16 columns per K-step
+//     SMEM  grad_y staging ring 132 KB  |  2 x 4 x (hi,mid) shifted waveform tiles, 26 KB  |  finalize scratch 13 KB
 // The accumulators are flushed every F2_FLUSH tiles (read-modify-write of the CTA's own partial tile in the
 // workspace), which bounds the length of any fp32 accumulation chain; see the issuer for why the flush does not
 // overlap the next window's MMAs.
