@@ -185,3 +185,27 @@ def test_bench_reference_arm_runs_on_cpu_and_ours_refuses_without_a_gpu():
         q = subprocess.run([sys.executable, bench, "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
         assert q.returncode != 0 and "no CPU fallback" in (q.stdout + q.stderr)
         assert not [l for l in q.stdout.splitlines() if l.startswith("{")]
+
+
+def test_bench_reference_arm_picks_a_thread_count_that_fits_the_host():
+    """The reference arm times the reference 'with all the host threads it can use' -- which is not one thread per visible
+    CPU on every box (the 32-CPU multi-GPU leases of this pool ran it 10x slower that way): the count is calibrated."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench as bench_module
+    n = bench_module.usable_cpus()
+    assert 1 <= n <= (os.cpu_count() or 1)
+    cls, _ = bench_module.reference_module_class()
+    before = torch.get_num_threads()
+    try:
+        best = bench_module.best_cpu_threads(cls, 16000)
+        assert 1 <= best <= n
+        assert line_cores_ok(bench_module, best)
+    finally:
+        torch.set_num_threads(before)
+
+
+def line_cores_ok(bench_module, best):
+    # the `cores` the JSON line reports is what torch really runs with after the calibration
+    torch.set_num_threads(best)
+    return torch.get_num_threads() == best
